@@ -1,0 +1,57 @@
+// Batched per-path fits: B independent paths of equal length N.  All paths advance together
+// through batched launches (grid.y = path) of the same kernels the single-matrix path uses:
+// covariance (lower tiles) -> blocked Cholesky with look-ahead -> blocked solves -> LML.
+#include "gemm.cuh"
+
+namespace gpm {
+
+int launch_cov(const double* X, long long N, int D, const Theta& th, double* K, long long ldk,
+               int lower_only, int batch, long long batch_x, long long batch_k, cudaStream_t stream);
+int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, double* invD, int* info,
+                  int batch, long long batch_rows, cudaStream_t s0);
+int solve_blocked(const double* L, long long N, long long ldl, const double* invD, double* alpha, int R,
+                  int batch, long long batch_l, long long batch_inv, long long batch_z, cudaStream_t stream);
+int launch_lml(const double* L, long long N, long long ldl, const double* Y, const double* alpha, int R,
+               double* lml, int batch, long long batch_l, long long batch_y, cudaStream_t stream);
+
+static inline long long round_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
+
+}  // namespace gpm
+
+using namespace gpm;
+
+extern "C" size_t gpm_fit_batched_workspace_bytes(int64_t B, int64_t N) {
+  if (B <= 0 || N <= 0) return 0;
+  const long long np = round_up_ll(N, NB);
+  return (size_t)B * (size_t)(np * np + np * NB) * sizeof(double);
+}
+
+extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const double* Yb, int64_t B, int64_t N,
+                               int32_t D, int32_t R, const double* theta, int64_t theta_stride,
+                               double* alpha, double* lml, int32_t* info, void* ws, gpm_stream_t stream) {
+  GPM_ARG(handle != nullptr, 1);
+  GPM_ARG(Xb != nullptr, 2);
+  GPM_ARG(Yb != nullptr, 3);
+  GPM_ARG(B > 0 && B <= 65535, 4);
+  GPM_ARG(N > 0 && B * ((N + NB - 1) / NB * NB) < (1ll << 31), 5);
+  Theta th;
+  GPM_ARG(make_theta(theta, D, &th) == 0, 8);
+  GPM_ARG(R >= 1 && R <= 8, 7);
+  GPM_ARG(theta_stride == 0, 9);       /* per-path theta: not implemented in this round */
+  GPM_ARG(alpha != nullptr && alpha != Yb, 10);
+  GPM_ARG(info != nullptr, 12);
+  GPM_ARG(ws != nullptr && ((uintptr_t)ws & 15) == 0, 13);
+  gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long np = round_up_ll(N, NB);
+  const int nblk = (int)(np / NB);
+  double* Kb = reinterpret_cast<double*>(ws);            // B stacked np x np matrices, ld = np
+  double* invD = Kb + (long long)B * np * np;            // B x nblk x NB x NB
+  int rc;
+  if ((rc = launch_cov(Xb, N, D, th, Kb, np, 1, (int)B, N * D, np * np, st))) return rc;
+  if ((rc = potrf_blocked(h, Kb, N, np, invD, info, (int)B, np, st))) return rc;
+  GPM_CUDA(cudaMemcpyAsync(alpha, Yb, (size_t)B * N * R * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if ((rc = solve_blocked(Kb, N, np, invD, alpha, R, (int)B, np * np, (long long)nblk * NB * NB, N * R, st))) return rc;
+  if (lml) return launch_lml(Kb, N, np, Yb, alpha, R, lml, (int)B, np * np, N * R, st);
+  return 0;
+}

@@ -1,0 +1,226 @@
+// Step 1 / 4 kernels: fused distance+exp covariance K(X,X)+sn2*I (symmetric-tile trick: each
+// off-diagonal 64x64 tile is evaluated once and stored twice, direct and transposed, both
+// coalesced), the materialised query-major cross-covariance, and the fused posterior mean.
+// CUDA cores only: the input dimension is 2-3, there is no contraction to give a tensor core.
+#include "common.cuh"
+
+namespace gpm {
+
+constexpr int CT = 64;            // covariance tile edge
+constexpr int CT_LD = CT + 1;     // padded smem pitch
+
+template <int D>
+__global__ void __launch_bounds__(256)
+cov_kernel(const double* __restrict__ X, long long N, Theta th, double* __restrict__ K,
+           long long ldk, int lower_only, long long batch_x, long long batch_k) {
+  __shared__ double xi[CT][3], xj[CT][3];
+  __shared__ double tile[CT][CT_LD];
+  // lower-triangular tile enumeration
+  const int b = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+  while ((ti + 1) * (ti + 2) / 2 <= b) ti++;
+  while (ti * (ti + 1) / 2 > b) ti--;
+  const int tj = b - ti * (ti + 1) / 2;
+  X += blockIdx.y * batch_x;
+  K += blockIdx.y * batch_k;
+  const long long i0 = (long long)ti * CT, j0 = (long long)tj * CT;
+  const int tid = threadIdx.x;
+  if (tid < CT * D) {
+    const int r = tid / D, d = tid % D;
+    xi[r][d] = (i0 + r < N) ? X[(i0 + r) * D + d] / th.l[d] : 0.0;
+  } else if (tid >= 128 && tid < 128 + CT * D) {
+    const int r = (tid - 128) / D, d = (tid - 128) % D;
+    xj[r][d] = (j0 + r < N) ? X[(j0 + r) * D + d] / th.l[d] : 0.0;
+  }
+  __syncthreads();
+  const int c2 = (tid & 31) * 2;
+  const bool diag = (ti == tj);
+  const bool mirror = !diag && (!lower_only || (ti >> 1) == (tj >> 1));
+  double bj0[3], bj1[3];
+#pragma unroll
+  for (int d = 0; d < D; d++) { bj0[d] = xj[c2][d]; bj1[d] = xj[c2 + 1][d]; }
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    const int r = (tid >> 5) + 8 * p;
+    double a[3];
+#pragma unroll
+    for (int d = 0; d < D; d++) a[d] = xi[r][d];
+    double v0 = rbf<D>(a, bj0, th.sf2), v1 = rbf<D>(a, bj1, th.sf2);
+    const long long gi = i0 + r, gj = j0 + c2;
+    if (gi == gj) v0 += th.sn2;
+    if (gi == gj + 1) v1 += th.sn2;
+    if (mirror) { tile[r][c2] = v0; tile[r][c2 + 1] = v1; }
+    if (gi < N) {
+      double* dst = K + gi * ldk + gj;
+      if (gj + 1 < N) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+      else if (gj < N) *dst = v0;
+    }
+  }
+  if (mirror) {
+    __syncthreads();
+    const int c = tid & 63;
+#pragma unroll
+    for (int p = 0; p < 16; p++) {
+      const int r = (tid >> 6) + 4 * p;               // row of the transposed tile = column of the direct one
+      const long long gi = j0 + r, gj = i0 + c;
+      if (gi < N && gj < N) K[gi * ldk + gj] = tile[c][r];
+    }
+  }
+}
+
+// KsT[m, i] = k(xs_m, x_i); 32 query rows x 256 training columns per CTA; columns [N, ncols_pad) zeroed.
+template <int D>
+__global__ void __launch_bounds__(256)
+cross_cov_t_kernel(const double* __restrict__ X, long long N, Theta th, const double* __restrict__ Xs,
+                   gpm_grid_t grid, int use_grid, long long m0, long long M, double* __restrict__ KsT,
+                   long long ldks, long long ncols_pad) {
+  __shared__ double q[32][3];
+  const int tid = threadIdx.x;
+  const long long mb = (long long)blockIdx.y * 32;
+  if (tid < 32) {
+    const long long m = mb + tid;
+    double c[3] = {0.0, 0.0, 0.0};
+    if (m < M) {
+      if (use_grid) { grid_point(grid, m0 + m, c[0], c[1]); c[2] = grid.t; }
+      else { for (int d = 0; d < D; d++) c[d] = Xs[(m0 + m) * D + d]; }
+    }
+#pragma unroll
+    for (int d = 0; d < D; d++) q[tid][d] = c[d] / th.l[d];
+  }
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * 256 + tid;
+  if (i >= ncols_pad) return;
+  double xi[3] = {0.0, 0.0, 0.0};
+  if (i < N) {
+#pragma unroll
+    for (int d = 0; d < D; d++) xi[d] = X[i * D + d] / th.l[d];
+  }
+#pragma unroll 4
+  for (int r = 0; r < 32; r++) {
+    const long long m = mb + r;
+    if (m >= M) break;
+    double v = 0.0;
+    if (i < N) v = rbf<D>(q[r], xi, th.sf2);
+    KsT[m * ldks + i] = v;
+  }
+}
+
+// mu[m, r] = sum_i k(xs_m, x_i) alpha[i, r]: one thread per query, training points and alpha staged
+// through shared memory in chunks; K* is never stored.
+template <int D, int RR>
+__global__ void __launch_bounds__(256)
+predict_mean_kernel(const double* __restrict__ X, long long N, Theta th, const double* __restrict__ alpha,
+                    int R, const double* __restrict__ Xs, gpm_grid_t grid, int use_grid, long long m0,
+                    long long M, double* __restrict__ mu) {
+  constexpr int CH = 512;
+  __shared__ double sx[CH][3];
+  __shared__ double sa[CH][RR];
+  const int tid = threadIdx.x;
+  const long long m = (long long)blockIdx.x * 256 + tid;
+  double c[3] = {0.0, 0.0, 0.0};
+  if (m < M) {
+    if (use_grid) { grid_point(grid, m0 + m, c[0], c[1]); c[2] = grid.t; }
+    else { for (int d = 0; d < D; d++) c[d] = Xs[(m0 + m) * D + d]; }
+  }
+  double qs[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) qs[d] = d < D ? c[d] / th.l[d] : 0.0;
+  double acc[RR];
+#pragma unroll
+  for (int r = 0; r < RR; r++) acc[r] = 0.0;
+  for (long long i0 = 0; i0 < N; i0 += CH) {
+    const int n = (int)((N - i0) < CH ? (N - i0) : CH);
+    __syncthreads();
+    for (int e = tid; e < n * D; e += 256) { const int r = e / D, d = e % D; sx[r][d] = X[(i0 + r) * D + d] / th.l[d]; }
+    for (int e = tid; e < n * RR; e += 256) { const int r = e / RR, k = e % RR; sa[r][k] = k < R ? alpha[(i0 + r) * R + k] : 0.0; }
+    __syncthreads();
+    for (int i = 0; i < n; i++) {
+      const double kv = rbf<D>(qs, sx[i], th.sf2);
+#pragma unroll
+      for (int r = 0; r < RR; r++) acc[r] = fma(kv, sa[i][r], acc[r]);
+    }
+  }
+  if (m < M) {
+#pragma unroll
+    for (int r = 0; r < RR; r++) if (r < R) mu[m * R + r] = acc[r];
+  }
+}
+
+int launch_cov(const double* X, long long N, int D, const Theta& th, double* K, long long ldk,
+               int lower_only, int batch, long long batch_x, long long batch_k, cudaStream_t stream) {
+  const int T = (int)((N + CT - 1) / CT);
+  dim3 grid(T * (T + 1) / 2, batch);
+  if (D == 2) cov_kernel<2><<<grid, 256, 0, stream>>>(X, N, th, K, ldk, lower_only, batch_x, batch_k);
+  else cov_kernel<3><<<grid, 256, 0, stream>>>(X, N, th, K, ldk, lower_only, batch_x, batch_k);
+  GPM_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_cross_cov_t(const double* X, long long N, int D, const Theta& th, const double* Xs,
+                       const gpm_grid_t* grid, long long m0, long long M, double* KsT, long long ldks,
+                       long long ncols_pad, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  gpm_grid_t g = {};
+  if (grid) g = *grid;
+  const int use_grid = Xs == nullptr;
+  dim3 gridDim((unsigned)((ncols_pad + 255) / 256), (unsigned)((M + 31) / 32));
+  if (D == 2) cross_cov_t_kernel<2><<<gridDim, 256, 0, stream>>>(X, N, th, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad);
+  else cross_cov_t_kernel<3><<<gridDim, 256, 0, stream>>>(X, N, th, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad);
+  GPM_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int D>
+static int launch_mean_d(const double* X, long long N, const Theta& th, const double* alpha, int R,
+                         const double* Xs, const gpm_grid_t& g, int use_grid, long long m0, long long M,
+                         double* mu, cudaStream_t stream) {
+  const unsigned blocks = (unsigned)((M + 255) / 256);
+  if (R <= 1) predict_mean_kernel<D, 1><<<blocks, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, mu);
+  else if (R <= 2) predict_mean_kernel<D, 2><<<blocks, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, mu);
+  else if (R <= 4) predict_mean_kernel<D, 4><<<blocks, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, mu);
+  else predict_mean_kernel<D, 8><<<blocks, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, mu);
+  GPM_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_predict_mean(const double* X, long long N, int D, const Theta& th, const double* alpha, int R,
+                        const double* Xs, const gpm_grid_t* grid, long long m0, long long M, double* mu,
+                        cudaStream_t stream) {
+  if (M <= 0) return 0;
+  gpm_grid_t g = {};
+  if (grid) g = *grid;
+  const int use_grid = Xs == nullptr;
+  return D == 2 ? launch_mean_d<2>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, mu, stream)
+                : launch_mean_d<3>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, mu, stream);
+}
+
+}  // namespace gpm
+
+using namespace gpm;
+
+extern "C" int gpm_cov(gpm_handle_t h, const double* X, int64_t N, int32_t D, const double* theta,
+                       double* K, int64_t ldk, int32_t flags, gpm_stream_t stream) {
+  GPM_ARG(h != nullptr, 1);
+  GPM_ARG(X != nullptr, 2);
+  GPM_ARG(N > 0 && N <= (1 << 20), 3);
+  Theta th;
+  GPM_ARG(make_theta(theta, D, &th) == 0, 5);
+  GPM_ARG(K != nullptr && ((uintptr_t)K & 15) == 0, 6);
+  GPM_ARG(ldk >= N && (ldk & 1) == 0, 7);
+  return launch_cov(X, N, D, th, K, ldk, (flags & GPM_COV_LOWER) ? 1 : 0, 1, 0, 0, (cudaStream_t)stream);
+}
+
+extern "C" int gpm_cross_cov(gpm_handle_t h, const double* X, int64_t N, int32_t D, const double* theta,
+                             const double* Xs, const gpm_grid_t* grid, int64_t m0, int64_t m1,
+                             double* KsT, int64_t ldks, gpm_stream_t stream) {
+  GPM_ARG(h != nullptr, 1);
+  GPM_ARG(X != nullptr, 2);
+  GPM_ARG(N > 0, 3);
+  Theta th;
+  GPM_ARG(make_theta(theta, D, &th) == 0, 5);
+  GPM_ARG(Xs != nullptr || grid != nullptr, 6);
+  GPM_ARG(m0 >= 0 && m1 >= m0, 8);
+  GPM_ARG(KsT != nullptr, 10);
+  GPM_ARG(ldks >= N, 11);
+  return launch_cross_cov_t(X, N, D, th, Xs, grid, m0, m1 - m0, KsT, ldks, N, (cudaStream_t)stream);
+}

@@ -1,0 +1,37 @@
+// FP64 tensor-core tile GEMM (NT form) used by the blocked Cholesky, the blocked TRSM of the
+// posterior variance and the batched fits:   C_tile (op)= A_rows * B_rows^T
+// where both operands are row-major with the contraction index contiguous.
+#pragma once
+#include "common.cuh"
+
+namespace gpm {
+
+enum { EPI_STORE = 0, EPI_SUB = 1 };
+
+struct GemmArgs {
+  double* C;              // output matrix
+  long long ldc;
+  double* rowsq;          // optional: rowsq[c_row] += sum over the tile's columns of out^2
+  int tiles_m, tiles_n;   // tile grid; with tri != 0 only tiles ti >= tj of a tiles_m x tiles_m grid
+  int tri;
+  int a_row0, a_col0;     // element origin of tile (0,*) in A and of the contraction range
+  int b_row0, b_col0;     // element origin of tile (*,0) in B
+  int b_tile_rows;        // B rows advance per tj (NB, or 0 when every tile uses the same B block)
+  int klen;               // contraction length (multiple of SLAB_K)
+  long long c_row0, c_col0;          // origin of tile (0,0) in C
+  long long c_rows_end, c_cols_end;  // exclusive store bounds in C
+  int epi;                // EPI_STORE: C = acc;  EPI_SUB: C = C - acc
+  // batch (blockIdx.y): rows added per batch index to A, B and C
+  long long batch_a_rows, batch_b_rows, batch_c_rows;
+  long long batch_rowsq;
+};
+
+// number of CTAs along x for the given args
+inline int gemm_grid_x(const GemmArgs& a) {
+  return a.tri ? a.tiles_m * (a.tiles_m + 1) / 2 : a.tiles_m * a.tiles_n;
+}
+
+int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& mapB,
+                const GemmArgs& args, int batch, cudaStream_t stream);
+
+}  // namespace gpm

@@ -1,0 +1,265 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via the GPmap drop-in module) against the
+numpy/scipy oracle and the committed golden vectors.  Tolerances are BASELINE.json's: 1e-8 on the
+posterior mean, 1e-6 on the variance, both norm-wise relative (max|d| / max|ref|); LML 1e-10 relative.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import gp_ref                                                      # noqa: E402
+from gaussianprocesspathmodelling_b200 import GPmap, _native, workloads as wl  # noqa: E402
+
+MEAN_TOL, VAR_TOL, LML_TOL = 1e-8, 1e-6, 1e-10
+
+
+def nrm(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_cov(X, th, lower=False):
+    lib = _native.load(); h = _native.handle(0)
+    N, D = X.shape
+    ld = (N + 15) // 16 * 16
+    K = torch.full((N, ld), float("nan"), dtype=torch.float64, device="cuda")
+    Xd = dev(X)
+    rc = lib.gpm_cov(h, C.c_void_p(Xd.data_ptr()), N, D, _native.theta_array(th), C.c_void_p(K.data_ptr()), ld,
+                     1 if lower else 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _native.check(rc, "gpm_cov")
+    torch.cuda.synchronize()
+    return K[:, :N].cpu().numpy()
+
+
+def gpu_potrf(Knp):
+    lib = _native.load(); h = _native.handle(0)
+    N = Knp.shape[0]
+    ld = (N + 15) // 16 * 16
+    K = torch.zeros((N, ld), dtype=torch.float64, device="cuda")
+    K[:, :N] = dev(Knp)
+    ws = torch.empty(int(lib.gpm_potrf_workspace_bytes(N)) // 8, dtype=torch.float64, device="cuda")
+    info = torch.full((1,), -7, dtype=torch.int32, device="cuda")
+    rc = lib.gpm_potrf(h, C.c_void_p(K.data_ptr()), N, ld, C.c_void_p(ws.data_ptr()), C.c_void_p(info.data_ptr()),
+                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _native.check(rc, "gpm_potrf")
+    torch.cuda.synchronize()
+    return np.tril(K[:, :N].cpu().numpy()), ws, int(info.item())
+
+
+@pytest.mark.parametrize("N,D", [(1, 2), (33, 2), (33, 3), (64, 2), (65, 3), (200, 2), (511, 3), (1000, 2)])
+def test_cov_matches_oracle(N, D):
+    X, _, th = wl.single_path(N, seed=100 + N, D=D)
+    K = gpu_cov(X, th)
+    Ko = gp_ref.cov(X, th)
+    assert np.abs(K - Ko).max() < 4e-15          # entries are <= 1.01; exp() implementations differ by < 1 ulp
+    assert np.array_equal(K, K.T)                # mirrored tiles are bitwise symmetric
+    Kl = gpu_cov(X, th, lower=True)
+    assert np.array_equal(np.tril(Kl), np.tril(K))
+
+
+@pytest.mark.parametrize("N", [1, 33, 128, 129, 200, 256, 300, 511, 1000, 1537])
+def test_potrf_matches_scipy(N):
+    X, _, th = wl.single_path(N, seed=200 + N, D=2)
+    Ko = gp_ref.cov(X, th)
+    L, ws, info = gpu_potrf(Ko)
+    assert info == 0
+    Lo = scipy.linalg.cholesky(Ko, lower=True)
+    assert np.abs(L @ L.T - Ko).max() / np.abs(Ko).max() < 1e-14
+    assert nrm(L, Lo) < 1e-11
+    # inverted diagonal blocks
+    nblk = (N + 127) // 128
+    inv = ws.cpu().numpy().reshape(nblk, 128, 128)
+    for k in range(nblk):
+        nv = min(128, N - 128 * k)
+        blk = Lo[128 * k:128 * k + nv, 128 * k:128 * k + nv]
+        assert np.abs(inv[k][:nv, :nv] @ blk - np.eye(nv)).max() < 1e-11
+        assert np.array_equal(inv[k][nv:, nv:], np.eye(128 - nv))
+
+
+def test_potrf_lookahead_equals_plain():
+    X, _, th = wl.single_path(900, seed=5, D=2)
+    Ko = gp_ref.cov(X, th)
+    L1, _, _ = gpu_potrf(Ko)
+    os.environ["GPM_NO_LOOKAHEAD"] = "1"
+    try:
+        L2, _, _ = gpu_potrf(Ko)
+    finally:
+        del os.environ["GPM_NO_LOOKAHEAD"]
+    assert np.array_equal(L1, L2)                # same kernels, same order of arithmetic
+
+
+def test_potrf_reports_non_positive_pivot():
+    A = np.eye(300); A[150, 150] = -1.0
+    _, _, info = gpu_potrf(A)
+    assert info == 151
+    B = np.eye(40); B[3, 3] = 0.0
+    assert gpu_potrf(B)[2] == 4
+    with pytest.raises(np.linalg.LinAlgError):
+        GPmap.fit_gp(np.zeros((5, 2)), np.ones(5), lengthscale=1.0, noise_var=0.0)   # singular: all points equal
+
+
+@pytest.mark.parametrize("tag,D", [("n33d2", 2), ("n33d3", 3)])
+def test_fit_predict_golden_n33(golden, tag, D):
+    X, Y, th = golden[f"{tag}_X"], golden[f"{tag}_Y"], golden[f"{tag}_theta"]
+    m = GPmap.fit_gp(X, Y, theta=th)
+    assert nrm(np.tril(m.L.cpu().numpy()), golden[f"{tag}_L"]) < 1e-12
+    assert nrm(m.alpha.cpu().numpy(), golden[f"{tag}_alpha"]) < MEAN_TOL
+    assert np.abs(m.lml - golden[f"{tag}_lml"]).max() < LML_TOL * np.abs(golden[f"{tag}_lml"]).max()
+    mu, var = m.predict_grid(wl.BOX, (9, 7), t=7.5 if D == 3 else None)
+    assert mu.shape == (7, 9, 2) and var.shape == (7, 9)
+    assert nrm(mu.cpu().numpy(), golden[f"{tag}_mu"]) < MEAN_TOL
+    assert nrm(var.cpu().numpy(), golden[f"{tag}_var"]) < VAR_TOL
+
+
+def test_config1_golden(golden):
+    X, Y, th = wl.single_path(200, seed=1, D=2, R=2)
+    m = GPmap.fit_gp(X, Y, lengthscale=8000.0, signal_var=1.0, noise_var=1e-2)
+    assert nrm(m.alpha.cpu().numpy(), golden["cfg1_alpha"]) < MEAN_TOL
+    assert np.abs(m.lml - golden["cfg1_lml"]).max() < LML_TOL * np.abs(golden["cfg1_lml"]).max()
+    mu, var = m.predict_grid(wl.BOX, (100, 100))
+    assert nrm(mu.cpu().numpy(), golden["cfg1_mu"]) < MEAN_TOL
+    assert nrm(var.cpu().numpy(), golden["cfg1_var"]) < VAR_TOL
+    # and against scikit-learn's independent numbers
+    assert nrm(mu.cpu().numpy()[:, :, 0], golden["cfg1_sk_mu0"]) < MEAN_TOL
+    assert nrm(var.cpu().numpy(), golden["cfg1_sk_var"]) < VAR_TOL
+    # mean-only path and predictive (noisy) variance
+    mu2 = m.predict_grid(wl.BOX, (100, 100), return_var=False)
+    assert torch.equal(mu2, mu)
+    _, var_y = m.predict_grid(wl.BOX, (100, 100), include_noise=True)
+    assert torch.allclose(var_y, var + 1e-2, rtol=0, atol=1e-15)
+
+
+def test_ragged_n300_scattered_queries_golden(golden):
+    X, Y, th = wl.single_path(300, seed=12, D=3, R=1)
+    m = GPmap.fit_gp(X, Y, theta=th)
+    assert nrm(m.alpha.cpu().numpy(), golden["n300_alpha"]) < MEAN_TOL
+    assert abs(m.lml[0] - golden["n300_lml"][0]) < LML_TOL * abs(golden["n300_lml"][0])
+    mu, var = m.predict(golden["n300_Xs"])
+    assert nrm(mu.cpu().numpy(), golden["n300_mu"]) < MEAN_TOL
+    assert nrm(var.cpu().numpy(), golden["n300_var"]) < VAR_TOL
+
+
+@pytest.mark.parametrize("N,D,R,M", [(1, 2, 1, 5), (2, 3, 2, 130), (127, 2, 1, 1), (128, 2, 3, 128), (129, 3, 2, 300),
+                                      (700, 2, 8, 1000), (1100, 3, 1, 257)])
+def test_fit_predict_vs_oracle_ragged(N, D, R, M):
+    rng = np.random.default_rng(N * 7 + D)
+    X, Y2, th = wl.single_path(max(N, 4), seed=300 + N, D=D, R=2)
+    X = X[:N]
+    Y = rng.standard_normal((N, R))
+    Xs = np.column_stack([rng.uniform(-5e4, 5e4, M), rng.uniform(-5e4, 5e4, M)] + ([rng.uniform(0, 50, M)] if D == 3 else []))
+    mo = gp_ref.fit(X, Y, th)
+    mu_o, var_o = gp_ref.predict(mo, Xs)
+    m = GPmap.fit_gp(X, Y, theta=th)
+    assert nrm(m.alpha.cpu().numpy(), mo["alpha"]) < MEAN_TOL
+    assert np.abs(m.lml - mo["lml"]).max() < LML_TOL * np.abs(mo["lml"]).max()
+    mu, var = m.predict(Xs)
+    assert nrm(mu.cpu().numpy(), mu_o) < MEAN_TOL
+    assert nrm(var.cpu().numpy(), var_o) < VAR_TOL
+
+
+def test_grid_sharding_concatenates_to_the_full_grid():
+    X, Y, th = wl.single_path(260, seed=9, D=2, R=2)
+    m = GPmap.fit_gp(X, Y, theta=th)
+    mu, var = m.predict_grid(wl.BOX, (37, 23))
+    from gaussianprocesspathmodelling_b200.dist import shard_range
+    parts = [m.predict_grid(wl.BOX, (37, 23), points=shard_range(37 * 23, r, 3)) for r in range(3)]
+    assert torch.equal(torch.cat([p[0] for p in parts]), mu.view(-1, 2))
+    assert torch.allclose(torch.cat([p[1] for p in parts]), var.view(-1), rtol=0, atol=1e-13)
+
+
+def test_batched_golden_and_oracle(golden):
+    Xb, Yb, th = wl.batched_paths(6, 130, seed=3, D=3, R=2)
+    alpha, lml = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+    assert nrm(alpha.cpu().numpy(), golden["b6_alpha"]) < MEAN_TOL
+    assert np.abs(lml.cpu().numpy() - golden["b6_lml"]).max() < LML_TOL * np.abs(golden["b6_lml"]).max()
+    Xb, Yb, th = wl.batched_paths(5, 512, seed=3, D=3, R=2, first=40)
+    alpha, lml = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+    a_o, l_o = gp_ref.fit_batched(Xb, Yb, th)
+    assert nrm(alpha.cpu().numpy(), a_o) < MEAN_TOL
+    assert np.abs(lml.cpu().numpy() - l_o).max() < LML_TOL * np.abs(l_o).max()
+    # a batched fit equals the single fits
+    one = GPmap.fit_gp(Xb[2], Yb[2], theta=th)
+    assert nrm(alpha[2].cpu().numpy(), one.alpha.cpu().numpy()) < 1e-12
+
+
+def test_lml_sweep_vs_oracle():
+    X, Y, _ = wl.single_path(180, seed=5, D=2, R=2)
+    ths = wl.sweep_thetas(D=2)[::9]
+    got = GPmap.lml_sweep(X, Y, ths)
+    want = gp_ref.lml_sweep(X, Y, ths)
+    assert np.abs(got - want).max() < 1e-9 * np.abs(want).max()
+
+
+def test_kmeans_assign_matches_reference(ref_golden):
+    g = ref_golden
+    T = GPmap.trajectories()
+    for i, k in enumerate(g["keys"].tolist()):
+        t = GPmap.trajectory(); t.xs, t.ys, t.timestamp = g["xs"][i], g["ys"][i], g["ts"][i]
+        T.add_trajectory(k, t)
+    cents = []
+    for c in range(len(g["group_sizes"])):
+        t = GPmap.trajectory(); t.xs, t.ys, t.timestamp = g["cx"][c], g["cy"][c], g["ct"][c]
+        cents.append(t)
+    assign, dist = T._assign(list(T.pathdict), cents)
+    assert np.array_equal(assign, g["assign"])
+    assert np.abs(dist - g["d2c"]).max() <= 1e-15 * g["d2c"].max()
+    clusters = T.kmeansclustering(3, seed=1)
+    assert sorted(k for v in clusters.values() for k in v) == sorted(T.pathdict)
+
+
+def test_config2_size_against_oracle_and_properties():
+    # N=4096 fit compared with the oracle directly (about a second of CPU), prediction on a strided
+    # sample of the 512x512 grid, plus size-independent properties of the full grid.
+    X, Y, th = wl.single_path(4096, seed=2, D=2, R=2)
+    m = GPmap.fit_gp(X, Y, theta=th)
+    mo = gp_ref.fit(X, Y, th)
+    assert nrm(np.tril(m.L.cpu().numpy()), mo["L"]) < 1e-9
+    assert np.abs(m.lml - mo["lml"]).max() < LML_TOL * np.abs(mo["lml"]).max()
+    Kd = dev(gp_ref.cov(X, th))
+    assert float((Kd @ m.alpha - dev(Y)).abs().max()) < 1e-9            # K alpha = Y
+    mu, var = m.predict_grid(wl.BOX, (512, 512))
+    P = gp_ref.grid_points(wl.BOX, (512, 512))
+    idx = np.arange(0, 512 * 512, 131)
+    mu_o, var_o = gp_ref.predict(mo, P[idx])
+    assert nrm(mu.view(-1, 2)[idx].cpu().numpy(), mu_o) < MEAN_TOL
+    assert nrm(var.view(-1)[idx].cpu().numpy(), var_o) < VAR_TOL
+    assert float(var.min()) > -1e-9 and float(var.max()) <= th[2] + 1e-12
+
+
+def test_config4_size_factor_properties():
+    # N=16384: L L^T reproduces K, and the factor agrees with cuSOLVER's (independent implementation)
+    X, Y, th = wl.single_path(16384, seed=4, D=2, R=1)
+    m = GPmap.fit_gp(X, Y, theta=th)
+    Kfull = torch.from_numpy(gpu_cov(X, th)).cuda()
+    L = m.L
+    resid = float((L @ L.T - Kfull).abs().max())
+    assert resid < 1e-12
+    Lc = torch.linalg.cholesky(Kfull)
+    assert float((L - Lc).abs().max()) / float(Lc.abs().max()) < 1e-9
+    a_c = torch.cholesky_solve(dev(Y), Lc)
+    assert float((m.alpha - a_c).abs().max()) / float(a_c.abs().max()) < 1e-6      # cond(K) ~ 1e6: alpha itself is loose
+    lml_c = -0.5 * float((dev(Y) * a_c).sum()) - float(torch.log(torch.diagonal(Lc)).sum()) - 8192 * np.log(2 * np.pi)
+    assert abs(m.lml[0] - lml_c) < LML_TOL * abs(lml_c)
+
+
+def test_c_abi_argument_errors():
+    lib = _native.load(); h = _native.handle(0)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    x = torch.zeros(8, 2, dtype=torch.float64, device="cuda"); k = torch.zeros(8, 8, dtype=torch.float64, device="cuda")
+    th = _native.theta_array([1.0, 1.0, 1.0, 0.1])
+    assert lib.gpm_cov(None, C.c_void_p(x.data_ptr()), 8, 2, th, C.c_void_p(k.data_ptr()), 8, 0, st) == -1
+    assert lib.gpm_cov(h, C.c_void_p(x.data_ptr()), 8, 4, th, C.c_void_p(k.data_ptr()), 8, 0, st) == -5
+    assert lib.gpm_cov(h, C.c_void_p(x.data_ptr()), 8, 2, th, C.c_void_p(k.data_ptr()), 7, 0, st) == -7
+    assert b"argument 7" in lib.gpm_last_error()
+    bad = _native.theta_array([1.0, -1.0, 1.0, 0.1])
+    assert lib.gpm_cov(h, C.c_void_p(x.data_ptr()), 8, 2, bad, C.c_void_p(k.data_ptr()), 8, 0, st) == -5
