@@ -25,12 +25,11 @@ cov_kernel(const double* __restrict__ X, long long N, Theta th, double* __restri
   K += blockIdx.y * batch_k;
   const long long i0 = (long long)ti * CT, j0 = (long long)tj * CT;
   const int tid = threadIdx.x;
-  if (tid < CT * D) {
-    const int r = tid / D, d = tid % D;
-    xi[r][d] = (i0 + r < N) ? X[(i0 + r) * D + d] / th.l[d] : 0.0;
-  } else if (tid >= 128 && tid < 128 + CT * D) {
-    const int r = (tid - 128) / D, d = (tid - 128) % D;
-    xj[r][d] = (j0 + r < N) ? X[(j0 + r) * D + d] / th.l[d] : 0.0;
+  for (int e = tid; e < 2 * CT * D; e += 256) {
+    const int which = e / (CT * D), r = (e % (CT * D)) / D, d = e % D;
+    const long long gr = (which ? j0 : i0) + r;
+    const double v = (gr < N) ? X[gr * D + d] / th.l[d] : 0.0;
+    if (which) xj[r][d] = v; else xi[r][d] = v;
   }
   __syncthreads();
   const int c2 = (tid & 31) * 2;
