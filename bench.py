@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""Benchmark of the GP path-modelling hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--no-extra]
+
+A "step" is one pass of the hot path over BASELINE.json config 2 (`configs[1]`): one GP with N=4096
+path samples, fit (covariance -> Cholesky -> alpha + LML) and posterior mean + variance on a 512x512
+grid.  metric = posterior grid points/s.  Under torchrun (N>1 ranks) every rank fits the (replicated,
+deterministic) model and evaluates its own 512x512 block of a 512 x (512*N) grid: weak scaling, no
+data-path collective.  `extra` carries the other two headline numbers of BASELINE.json's metric,
+measured in the same run: batched fits/s (config 3, 4096 paths x N=512 per GPU) and Cholesky TFLOP/s
+at N=16384 (config 4), plus per-kernel rooflines.
+
+`--impl reference`: the reference has no GP implementation, so this arm times the
+numpy/scipy oracle port of the same path on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "posterior grid points/sec (GP N=4096 fit + mean+variance on a 512x512 grid)"
+UNIT = "grid points/s"
+CFG = dict(N=4096, D=2, R=2, G=512, seed=2)
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback", "fp64_tflops": 37.0, "fp64_src": "nominal"}
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks["hbm_gbs"], peaks["hbm_src"] = float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_FP64.json")))
+        peaks["fp64_tflops"], peaks["fp64_src"] = float(p["dgemm_tflops_burst"]), "measured cuBLAS DGEMM 8192^3 (MEASURED_FP64.json)"
+        peaks["fp64_tflops_sustained"] = float(p["dgemm_tflops_sustained"])
+    except Exception:
+        pass
+    return peaks
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], 0.0, set(), 0.0
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx = max(mx, float(f[1]))
+                if t0 - 0.05 <= t <= t1 + 0.05:
+                    sm.append(float(f[0])); power = max(power, float(f[6]))
+                    for n, v in zip(names, f[2:6]):
+                        if v.lower().startswith("active"):
+                            reasons.add(n)
+            except ValueError:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": mx or None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": power}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample of config 2
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(n_query=16384, repeats=1):
+    """Oracle (numpy/scipy) on config 2: full fit + posterior on a sample of the grid, extrapolated to
+    the whole 512x512 grid.  Returns (points_per_s, detail)."""
+    from threadpoolctl import threadpool_info
+    from oracle import gp_ref
+    from gaussianprocesspathmodelling_b200 import workloads as wl
+    X, Y, th = wl.single_path(CFG["N"], CFG["seed"], CFG["D"], CFG["R"])
+    M = CFG["G"] ** 2
+    P = gp_ref.grid_points(wl.BOX, (CFG["G"], CFG["G"]))
+    idx = np.linspace(0, M - 1, n_query).astype(np.int64)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        m = gp_ref.fit(X, Y, th)
+        t1 = time.perf_counter()
+        gp_ref.predict(m, P[idx])
+        t2 = time.perf_counter()
+        cur = (t1 - t0, t2 - t1)
+        if best is None or sum(cur) < sum(best):
+            best = cur
+    t_fit, t_pred = best
+    est = t_fit + t_pred * (M / n_query)
+    cores = os.cpu_count()
+    try:
+        info = threadpool_info()
+        nthr = max([i.get("num_threads", 1) for i in info] or [1])
+    except Exception:
+        nthr = cores
+    detail = {"fit_s": t_fit, "predict_sample_s": t_pred, "sample_points": int(n_query),
+              "extrapolated_step_s": est, "blas_threads": nthr, "host_cores": cores}
+    return M / est, detail
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_sample(2048)
+    vals, det = [], None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, det = cpu_sample(8192)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": CFG["G"] ** 2 / v * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: N=4096 D=2 R=2, fit + mean+variance on 512x512 grid", "seed": CFG["seed"],
+                   "note": "reference has no GP code; numpy/scipy oracle port of the same path on host cores"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": det["blas_threads"], "kind": "port",
+                         "sample": f"full N=4096 fit + posterior on {det['sample_points']} of 262144 grid points per step, "
+                                   f"extrapolated linearly in the number of points; wall {wall:.1f}s"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def ev_pair(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def timed(torch, fn, reps, warm=1, flush=None):
+    """Mean CUDA-event time (ms) of fn on the current stream, after `warm` untimed calls."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(reps):
+        if flush is not None:
+            flush()
+        e0, e1 = ev_pair(torch)
+        e0.record(); fn(); e1.record(); e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+def run_b200(args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from gaussianprocesspathmodelling_b200 import GPmap, _native, workloads as wl
+    from gaussianprocesspathmodelling_b200.dist import shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    lib = _native.load()
+    h = _native.handle(local)
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    N, D, R, G = CFG["N"], CFG["D"], CFG["R"], CFG["G"]
+    X, Y, th = wl.single_path(N, CFG["seed"], D, R)
+    Xd, Yd = torch.from_numpy(X).to(dev), torch.from_numpy(Y).to(dev)
+    Gy_total = G * world                                 # weak scaling: the grid grows by 512 rows per GPU
+    y_lo, y_hi = wl.BOX[2], wl.BOX[3]
+    bounds = (wl.BOX[0], wl.BOX[1], y_lo, y_hi)
+    shape = (G, Gy_total)
+    lo, hi = shard_range(G * Gy_total, rank, world)
+    M_local = hi - lo
+
+    state = {}
+
+    def step_device():
+        m = GPmap.fit_gp(Xd, Yd, theta=th, check=False)
+        if "pws" in state:
+            m._pws = state["pws"]
+        mu, var = m.predict_grid(bounds, shape, points=(lo, hi))
+        state["pws"] = m._pws
+        state["out"] = (mu, var, m)
+
+    # ---- timed region 1: device-resident inputs -------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    clocks = Clocks(local)
+    clocks.start()
+    time.sleep(0.3)
+    launches0 = lib.gpm_launch_count()
+    barrier()
+    t0w = time.time()
+    e0, e1 = ev_pair(torch)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    t1w = time.time()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = (lib.gpm_launch_count() - launches0) // args.steps
+    clk = clocks.stop(t0w, t1w)
+    ms_step = ms_total / args.steps
+    value = (G * Gy_total) / (ms_step * 1e-3)
+    mu, var, model = state["out"]
+    info = int(model.info.item())
+
+    # ---- timed region 2: end to end through the public API with host buffers ---------------------
+    Xh = torch.from_numpy(X).pin_memory(); Yh = torch.from_numpy(Y).pin_memory()
+    mu_h = torch.empty((M_local, R), dtype=torch.float64).pin_memory()
+    var_h = torch.empty((M_local,), dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        xd = Xh.to(dev, non_blocking=True); yd = Yh.to(dev, non_blocking=True)
+        m = GPmap.fit_gp(xd, yd, theta=th, check=False)
+        m._pws = state["pws"]
+        mu_d, var_d = m.predict_grid(bounds, shape, points=(lo, hi))
+        mu_h.copy_(mu_d, non_blocking=True); var_h.copy_(var_d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return m
+
+    step_e2e()
+    barrier()
+    e0, e1 = ev_pair(torch)
+    e0.record()
+    for _ in range(args.steps):
+        m_last = step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_value = (G * Gy_total) / (ms_e2e * 1e-3)
+    h2d = Xh.numel() * 8 + Yh.numel() * 8
+    d2h = mu_h.numel() * 8 + var_h.numel() * 8
+    del m_last
+
+    # ---- per-kernel phases on this rank (CUDA events on the launching stream) ---------------------
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)   # noqa: E731
+    tha = _native.theta_array(th)
+    ld = (N + 15) // 16 * 16
+    K = torch.empty((N, ld), dtype=torch.float64, device=dev)
+    ws = torch.empty(int(lib.gpm_potrf_workspace_bytes(N)) // 8, dtype=torch.float64, device=dev)
+    infod = torch.zeros(1, dtype=torch.int32, device=dev)
+    alpha = torch.empty((N, R), dtype=torch.float64, device=dev)
+    lml = torch.empty((R,), dtype=torch.float64, device=dev)
+    grid = _native.GpmGrid(bounds[0], bounds[1], bounds[2], bounds[3], 0.0, G, Gy_total)
+    pws = state["pws"]
+    flushbuf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush():
+        flushbuf.zero_()
+
+    def k_cov(flags=0):
+        _native.check(lib.gpm_cov(h, ptr(Xd), N, D, tha, ptr(K), ld, flags, st), "cov")
+
+    def k_potrf():
+        _native.check(lib.gpm_potrf(h, ptr(K), N, ld, ptr(ws), ptr(infod), st), "potrf")
+
+    def k_solve():
+        _native.check(lib.gpm_solve_lml(h, ptr(K), N, ld, ptr(ws), ptr(Yd), R, ptr(alpha), ptr(lml), st), "solve")
+
+    def k_pred(flags):
+        _native.check(lib.gpm_predict(h, ptr(Xd), N, D, tha, ptr(K), ld, ptr(ws), ptr(alpha), R, None, C.byref(grid),
+                                      lo, hi, ptr(mu), ptr(var), ptr(pws), pws.numel() * 8, flags, st), "predict")
+
+    phases = {}
+    phases["cov_full_ms"] = timed(torch, lambda: k_cov(0), 5, flush=flush)
+    phases["cov_lower_ms"] = timed(torch, lambda: k_cov(1), 5, flush=flush)
+
+    def cov_potrf():
+        k_cov(1); k_potrf()
+    t_cp = timed(torch, cov_potrf, 5, flush=flush)
+    phases["potrf_ms"] = t_cp - phases["cov_lower_ms"]
+    phases["solve_lml_ms"] = timed(torch, k_solve, 5, flush=flush)
+    nl0 = lib.gpm_launch_count()
+    phases["predict_var_ms"] = timed(torch, lambda: k_pred(2), 2, warm=1)
+    var_launches = (lib.gpm_launch_count() - nl0) // 3
+    phases["predict_mean_ms"] = timed(torch, lambda: k_pred(1), 3, warm=1)
+    nblk = (N + 127) // 128
+    chunks = max(1, var_launches // (2 * nblk + 1))          # per chunk: cross-cov + (2 nblk - 1) GEMMs + finalize
+    gemm_launches = var_launches - 2 * chunks
+    var_flops = float(N) * N * M_local
+    var_tflops = var_flops / (phases["predict_var_ms"] * 1e-3) / 1e12
+    roofline = {
+        "kernel": "gemm_nt_kernel (DMMA.8x8x4 + TMA) inside the blocked TRSM of the posterior variance",
+        "bound": "tensor", "achieved": var_tflops, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
+        "frac": var_tflops / peaks["fp64_tflops"], "traffic": None,
+        "peak_source": peaks["fp64_src"],
+        "launches_per_step": int(gemm_launches), "flops_per_launch": var_flops / max(1, gemm_launches),
+        "avg_launch_ms": phases["predict_var_ms"] / max(1, gemm_launches),
+        "note": "algorithmic flops N^2*M of V = L^-1 K*; time = CUDA events around the variance phase "
+                "(cross-cov write + all GEMM launches + finalize)",
+    }
+    kernels = {
+        "cov_full": {"bound": "hbm", "achieved": 8.0 * N * N / (phases["cov_full_ms"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"},
+        "potrf": {"bound": "tensor", "achieved": N ** 3 / 3 / (phases["potrf_ms"] * 1e-3) / 1e12, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s"},
+        "solve_lml": {"bound": "hbm", "achieved": 8.0 * N * N / (phases["solve_lml_ms"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"},
+        "predict_mean": {"bound": "fp64-exp", "achieved": float(N) * M_local / (phases["predict_mean_ms"] * 1e-3) / 1e9, "peak": None, "unit": "Gevals/s"},
+    }
+    for k in kernels.values():
+        k["frac"] = (k["achieved"] / k["peak"]) if k["peak"] else None
+
+    extra = {"phases_ms": phases, "kernels": kernels, "potrf_info": info}
+
+    # ---- the other two headline numbers: Cholesky TFLOP/s at N=16384, batched fits/s ---------------
+    if not args.no_extra:
+        del K, ws
+        state.clear(); pws = None; model = None
+        torch.cuda.empty_cache()
+        N4 = 16384
+        X4, Y4, th4 = wl.single_path(N4, 4, 2, 1)
+        X4d = torch.from_numpy(X4).to(dev)
+        K4 = torch.empty((N4, N4), dtype=torch.float64, device=dev)
+        ws4 = torch.empty(int(lib.gpm_potrf_workspace_bytes(N4)) // 8, dtype=torch.float64, device=dev)
+        th4a = _native.theta_array(th4)
+
+        def cov4(flags):
+            _native.check(lib.gpm_cov(h, ptr(X4d), N4, 2, th4a, ptr(K4), N4, flags, st), "cov")
+
+        def cp4():
+            cov4(1)
+            _native.check(lib.gpm_potrf(h, ptr(K4), N4, N4, ptr(ws4), ptr(infod), st), "potrf")
+        t_cov4 = timed(torch, lambda: cov4(0), 5, flush=flush)
+        t_cov4l = timed(torch, lambda: cov4(1), 5, flush=flush)
+        t_cp4 = timed(torch, cp4, 3, flush=flush)
+        t_potrf4 = t_cp4 - t_cov4l
+        y4 = torch.from_numpy(Y4).to(dev); a4 = torch.empty_like(y4); l4 = torch.empty(1, dtype=torch.float64, device=dev)
+        t_solve4 = timed(torch, lambda: _native.check(lib.gpm_solve_lml(h, ptr(K4), N4, N4, ptr(ws4), ptr(y4), 1, ptr(a4), ptr(l4), st), "solve"), 3, flush=flush)
+        extra["cfg4_N16384"] = {
+            "cov_ms": t_cov4, "cov_gbs": 8.0 * N4 * N4 / (t_cov4 * 1e-3) / 1e9, "cov_frac_hbm": 8.0 * N4 * N4 / (t_cov4 * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "potrf_ms": t_potrf4, "potrf_tflops": N4 ** 3 / 3 / (t_potrf4 * 1e-3) / 1e12,
+            "potrf_frac_dgemm": N4 ** 3 / 3 / (t_potrf4 * 1e-3) / 1e12 / peaks["fp64_tflops"],
+            "solve_lml_ms": t_solve4, "solve_gbs": 8.0 * N4 * N4 / (t_solve4 * 1e-3) / 1e9,
+            "info": int(infod.item()),
+        }
+        del K4, ws4
+        torch.cuda.empty_cache()
+        B = 4096
+        Xb, Yb, thb = wl.batched_paths(B, 512, seed=3, D=3, R=2, first=rank * B)
+        Xbd, Ybd = torch.from_numpy(Xb).to(dev), torch.from_numpy(Yb).to(dev)
+        t_b = timed(torch, lambda: GPmap.fit_gp_batched(Xbd, Ybd, theta=thb, check=False), 3, warm=1)
+        t_b = max_over_ranks(t_b)
+        extra["cfg3_batched"] = {"paths_per_gpu": B, "N": 512, "ms": t_b, "fits_per_s": world * B / (t_b * 1e-3),
+                                 "frac_of_fp64_ceiling": (world * B / (t_b * 1e-3)) * 5.1e7 / (world * peaks["fp64_tflops"] * 1e12)}
+
+    # ---- CPU baseline on this box (rank 0, N=1 only) --------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, det = cpu_sample(16384)
+        cpu = {"value": v, "unit": UNIT, "cores": det["blas_threads"], "kind": "port",
+               "sample": f"numpy/scipy oracle: full N=4096 fit ({det['fit_s']:.2f}s) + posterior on 16384 of 262144 grid points "
+                         f"({det['predict_sample_s']:.2f}s), extrapolated linearly to the whole grid",
+               "host_cores": det["host_cores"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"cfg2: GP N={N} D={D} R={R} (seed {CFG['seed']}), fit + posterior mean+variance on a "
+                                   f"{G}x{G} grid per GPU ({G}x{Gy_total} total)",
+                       "l2": "working set (K 134 MB, W 8.6 GB) exceeds the 126 MB L2; per-kernel phases flush L2 with a 256 MB write",
+                       "parallelism": f"grid rows sharded over {world} rank(s), model replicated, no data-path collective"},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "extra": extra,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the config-3 / config-4 side measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,7 @@ SIGNATURES = {
     "gpm_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "gpm_destroy": (C.c_int, [_vp]),
     "gpm_sm_count": (C.c_int, [_vp]),
+    "gpm_launch_count": (C.c_longlong, []),
     "gpm_cov": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double), _vp, _i64, _i32, _vp]),
     "gpm_cross_cov": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double), _vp, C.POINTER(GpmGrid), _i64, _i64,
                                 _vp, _i64, _vp]),

@@ -1,4 +1,5 @@
 // Handle, error text and TMA tensor-map construction for libgpmap_b200.
+#include <atomic>
 #include <stdarg.h>
 #include <string.h>
 
@@ -7,6 +8,9 @@
 namespace gpm {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -49,6 +53,8 @@ using namespace gpm;
 extern "C" {
 
 int gpm_version(void) { return GPM_VERSION; }
+
+long long gpm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* gpm_last_error(void) { return g_err; }
 

@@ -18,6 +18,7 @@ namespace gpm {
 // host-side error plumbing
 // ----------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+void count_launch(long long n);          // process-wide count of kernels this library launched
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define GPM_CUDA(call)                                                         \
@@ -28,6 +29,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define GPM_LAUNCH_CHECK()                                                     \
   do {                                                                         \
+    gpm::count_launch(1);                                                      \
     cudaError_t _e = cudaPeekAtLastError();                                    \
     if (_e != cudaSuccess) return gpm::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
   } while (0)

@@ -24,6 +24,8 @@ struct GemmArgs {
   // batch (blockIdx.y): rows added per batch index to A, B and C
   long long batch_a_rows, batch_b_rows, batch_c_rows;
   long long batch_rowsq;
+  int tiles_per_cta;      // filled by launch_gemm: consecutive tiles one CTA works through
+  int max_tiles_per_cta;  // 0 = default (16); the look-ahead Cholesky caps it so that SMs free up regularly
 };
 
 // number of CTAs along x for the given args
@@ -31,7 +33,8 @@ inline int gemm_grid_x(const GemmArgs& a) {
   return a.tri ? a.tiles_m * (a.tiles_m + 1) / 2 : a.tiles_m * a.tiles_n;
 }
 
+// mapC describes the matrix args.C points into (used to prefetch C tiles by TMA when epi == EPI_SUB)
 int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& mapB,
-                const GemmArgs& args, int batch, cudaStream_t stream);
+                const CUtensorMap& mapC, const GemmArgs& args, int batch, cudaStream_t stream);
 
 }  // namespace gpm

@@ -15,72 +15,135 @@
 
 namespace gpm {
 
-constexpr int PLD = NB + 1;   // padded smem pitch (doubles)
-constexpr int POTF2_SMEM = (NB * PLD + NB) * 8;
+constexpr int PLD = NB + 1;   // padded smem pitch (doubles) of the 128x128 block
+constexpr int XLD = 12;       // pitch of the 8-column panel staging buffer (conflict-free DMMA fragment reads)
+constexpr int POTF2_SMEM = (NB * PLD + NB * XLD + 16 * 64) * 8;
 
-// C(SxS block at [ro, co]) = sign * A(SxS at [ar, ac]) * B(SxS at [br, bc]), for 64/S independent
-// "pairs" laid out along the diagonal with period 2S; results are returned in registers so the
-// caller can overwrite one of the operands after a barrier.
-template <int S, int TR, int TC>
-__device__ __forceinline__ void smem_block_mm(const double* sm, int tid, int a_dr, int a_dc, int b_dr,
-                                              int b_dc, double (&out)[TR][TC], int& row0, int& col0,
-                                              int& pair_base) {
-  constexpr int TX = S / TC, TY = S / TR, TPP = TX * TY;
-  const int pair = tid / TPP, lt = tid % TPP;
-  const int ty = lt / TX, tx = lt % TX;
-  pair_base = pair * 2 * S;
-  row0 = ty;   // rows  ty + r*TY
-  col0 = tx;   // cols  tx + c*TX
+// One 8x8 lower-triangular factor + its inverse, entirely in one thread's registers.
+// a: packed lower (row-major, a[i*(i+1)/2 + j]); on exit a holds L, x holds inv(L) (same packing).
+// Returns the 1-based index of the first non-positive pivot (0 if none).
+__device__ __forceinline__ int chol8_inv(double (&a)[36], double (&x)[36]) {
+  // every loop has constant bounds 0..7 with compile-time-foldable guards, so that full unrolling
+  // keeps both arrays in registers
+  double r[8];
+  int bad = 0;
 #pragma unroll
-  for (int r = 0; r < TR; r++)
+  for (int j = 0; j < 8; j++) {
+    double d = a[j * (j + 1) / 2 + j];
 #pragma unroll
-    for (int c = 0; c < TC; c++) out[r][c] = 0.0;
-  const double* A = sm + (pair_base + a_dr) * PLD + pair_base + a_dc;
-  const double* B = sm + (pair_base + b_dr) * PLD + pair_base + b_dc;
-#pragma unroll 4
-  for (int k = 0; k < S; k++) {
-    double a[TR], b[TC];
+    for (int k = 0; k < 8; k++)
+      if (k < j) d = fma(-a[j * (j + 1) / 2 + k], a[j * (j + 1) / 2 + k], d);
+    if (!(d > 0.0) || !(d < 1.0e300)) { if (!bad) bad = j + 1; d = 1.0; }
+    const double ljj = sqrt(d);
+    r[j] = 1.0 / ljj;
+    a[j * (j + 1) / 2 + j] = ljj;
 #pragma unroll
-    for (int r = 0; r < TR; r++) a[r] = A[(ty + r * TY) * PLD + k];
+    for (int i = 0; i < 8; i++) {
+      if (i > j) {
+        double v = a[i * (i + 1) / 2 + j];
 #pragma unroll
-    for (int c = 0; c < TC; c++) b[c] = B[k * PLD + tx + c * TX];
-#pragma unroll
-    for (int r = 0; r < TR; r++)
-#pragma unroll
-      for (int c = 0; c < TC; c++) out[r][c] = fma(a[r], b[c], out[r][c]);
+        for (int k = 0; k < 8; k++)
+          if (k < j) v = fma(-a[i * (i + 1) / 2 + k], a[j * (j + 1) / 2 + k], v);
+        a[i * (i + 1) / 2 + j] = v * r[j];
+      }
+    }
   }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    x[j * (j + 1) / 2 + j] = r[j];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (i > j) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (k >= j && k < i) v = fma(a[i * (i + 1) / 2 + k], x[k * (k + 1) / 2 + j], v);
+        x[i * (i + 1) / 2 + j] = -v * r[i];
+      }
+    }
+  }
+  return bad;
 }
 
-// one level of the recursive-doubling triangular inverse: X21 = -X22 * (L21 * X11)
-template <int S, int TR, int TC>
-__device__ __forceinline__ void inv_level(double* sm, int tid) {
-  constexpr int TX = S / TC, TY = S / TR;
-  double t[TR][TC];
-  int r0, c0, pb;
-  smem_block_mm<S, TR, TC>(sm, tid, /*A=L21*/ S, 0, /*B=X11*/ 0, 0, t, r0, c0, pb);
+// One level of the recursive-doubling inverse on DMMA tiles:  X21 = -X22 * (L21 * X11)  for all
+// 64/S pairs of SxS diagonal blocks (X11, X22 already inverted in place, upper parts zero).
+template <int S>
+__device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
+  constexpr int TB = S / 8;                 // 8x8 tiles per block edge
+  constexpr int TILES = (NB / (2 * S)) * TB * TB;
+  constexpr int PER_WARP = (TILES + 7) / 8;
+  const int g = lane >> 2, q = lane & 3;
+  double c0[PER_WARP], c1[PER_WARP];
+  // phase 1: T = L21 * X11   (X11 lower: contraction blocks kb >= b)
+#pragma unroll
+  for (int e = 0; e < PER_WARP; e++) {
+    const int t = warp + 8 * e;
+    c0[e] = c1[e] = 0.0;
+    if (t < TILES) {
+      const int pair = t / (TB * TB), a = (t / TB) % TB, b = t % TB;
+      const int o1 = pair * 2 * S, o2 = o1 + S;
+      for (int k0 = 8 * b; k0 < S; k0 += 4) {
+        const double af = sm[(o2 + 8 * a + g) * PLD + o1 + k0 + q];
+        const double bf = sm[(o1 + k0 + q) * PLD + o1 + 8 * b + g];
+        dmma(c0[e], c1[e], af, bf);
+      }
+    }
+  }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < TR; r++)
-#pragma unroll
-    for (int c = 0; c < TC; c++) sm[(pb + S + r0 + r * TY) * PLD + pb + c0 + c * TX] = t[r][c];
+  for (int e = 0; e < PER_WARP; e++) {
+    const int t = warp + 8 * e;
+    if (t < TILES) {
+      const int pair = t / (TB * TB), a = (t / TB) % TB, b = t % TB;
+      const int o1 = pair * 2 * S, o2 = o1 + S;
+      double* dst = sm + (o2 + 8 * a + g) * PLD + o1 + 8 * b + 2 * q;
+      dst[0] = c0[e]; dst[1] = c1[e];
+    }
+  }
   __syncthreads();
-  smem_block_mm<S, TR, TC>(sm, tid, /*A=X22*/ S, S, /*B=T*/ S, 0, t, r0, c0, pb);
+  // phase 2: X21 = -X22 * T   (X22 lower: contraction blocks kb <= a)
+#pragma unroll
+  for (int e = 0; e < PER_WARP; e++) {
+    const int t = warp + 8 * e;
+    c0[e] = c1[e] = 0.0;
+    if (t < TILES) {
+      const int pair = t / (TB * TB), a = (t / TB) % TB, b = t % TB;
+      const int o1 = pair * 2 * S, o2 = o1 + S;
+      for (int k0 = 0; k0 < 8 * a + 8; k0 += 4) {
+        const double af = -sm[(o2 + 8 * a + g) * PLD + o2 + k0 + q];
+        const double bf = sm[(o2 + k0 + q) * PLD + o1 + 8 * b + g];
+        dmma(c0[e], c1[e], af, bf);
+      }
+    }
+  }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < TR; r++)
-#pragma unroll
-    for (int c = 0; c < TC; c++) sm[(pb + S + r0 + r * TY) * PLD + pb + c0 + c * TX] = -t[r][c];
+  for (int e = 0; e < PER_WARP; e++) {
+    const int t = warp + 8 * e;
+    if (t < TILES) {
+      const int pair = t / (TB * TB), a = (t / TB) % TB, b = t % TB;
+      const int o1 = pair * 2 * S, o2 = o1 + S;
+      double* dst = sm + (o2 + 8 * a + g) * PLD + o1 + 8 * b + 2 * q;
+      dst[0] = c0[e]; dst[1] = c1[e];
+    }
+  }
   __syncthreads();
 }
 
 // Factor diagonal block kblk of K in shared memory, write L_kk back and inv(L_kk) to invD.
 // Rows/columns beyond N are padded with the identity.  blockIdx.x = batch index.
+//
+// Right-looking over sixteen 8-column panels: (1) one thread factors and inverts the 8x8 diagonal
+// block in registers, (2) one thread per row solves the panel against it, (3) all warps apply the
+// rank-8 update to the trailing 8x8 tiles with two DMMA.8x8x4 each.  The 128x128 inverse is then
+// assembled from the 8x8 inverses by recursive doubling, also on DMMA tiles.
 __global__ void __launch_bounds__(256, 1)
 potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, double* __restrict__ invD,
                  int* __restrict__ info, long long batch_k, long long batch_inv) {
   extern __shared__ double sm[];
-  double* dg = sm + NB * PLD;
-  const int tid = threadIdx.x;
+  double* xp = sm + NB * PLD;          // [128][XLD] current panel
+  double* inv8 = xp + NB * XLD;        // [16][64]  inverses of the 8x8 diagonal blocks (full, zero upper)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   K += blockIdx.x * batch_k;
   invD += blockIdx.x * batch_inv + (long long)kblk * NB * NB;
   info += blockIdx.x;
@@ -96,62 +159,80 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
   }
   __syncthreads();
 
-  // ---- unblocked right-looking factorisation, 2 barriers per column; 16x16 cyclic thread grid ----
-  const int ty = tid >> 4, tx = tid & 15;
-  for (int j = 0; j < NB; j++) {
-    const double ajj = sm[j * PLD + j];
-    const bool bad = !(ajj > 0.0) || !(ajj < 1.0e300);
-    const double d = bad ? 1.0 : sqrt(ajj);
-    if (tid > j && tid < NB) sm[tid * PLD + j] /= d;
+  const int g = lane >> 2, q = lane & 3;
+  for (int p = 0; p < 16; p++) {
+    const int c0 = 8 * p;
+    // (1) 8x8 diagonal block: factor + invert in one thread
     if (tid == 0) {
-      dg[j] = d;
-      if (bad && j < nv) atomicCAS(info, 0, (int)(r0 + j + 1));
+      double a[36], x[36];
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) a[i * (i + 1) / 2 + j] = sm[(c0 + i) * PLD + c0 + j];
+      const int bad = chol8_inv(a, x);
+      if (bad && c0 + bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + c0 + bad));
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (j <= i) sm[(c0 + i) * PLD + c0 + j] = a[i * (i + 1) / 2 + j];
+          inv8[p * 64 + i * 8 + j] = (j <= i) ? x[i * (i + 1) / 2 + j] : 0.0;
+        }
     }
     __syncthreads();
-    const int jp = j + 1;
-    const int i0 = ty >= jp ? ty : ty + (((jp - ty) + 15) & ~15);
-    const int c0 = tx >= jp ? tx : tx + (((jp - tx) + 15) & ~15);
-    for (int i = i0; i < NB; i += 16) {
-      const double lij = sm[i * PLD + j];
-      for (int c = c0; c <= i; c += 16) sm[i * PLD + c] = fma(-lij, sm[c * PLD + j], sm[i * PLD + c]);
+    // (2) panel solve: X[i, 0:8] = A[i, c0:c0+8] * inv(L8)^T, one thread per row below the block
+    if (tid < NB && tid >= c0 + 8) {
+      double a[8], x[8];
+      double* row = sm + tid * PLD + c0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) a[k] = row[k];
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k <= c; k++) v = fma(a[k], inv8[p * 64 + c * 8 + k], v);
+        x[c] = v;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) { row[c] = x[c]; xp[tid * XLD + c] = x[c]; }
+    }
+    __syncthreads();
+    // (3) trailing update on 8x8 tiles: C[ti][tj] -= X_ti X_tj^T, two DMMAs per tile
+    const int nt = 15 - p, rb = c0 + 8;
+    const int ntiles = nt * (nt + 1) / 2;
+    for (int e = warp; e < ntiles; e += 8) {
+      int ti = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while ((ti + 1) * (ti + 2) / 2 <= e) ti++;
+      while (ti * (ti + 1) / 2 > e) ti--;
+      const int tj = e - ti * (ti + 1) / 2;
+      const double* xa = xp + (rb + 8 * ti + g) * XLD + q;
+      const double* xb = xp + (rb + 8 * tj + g) * XLD + q;
+      double* cp = sm + (rb + 8 * ti + g) * PLD + rb + 8 * tj + 2 * q;
+      double c0v = cp[0], c1v = cp[1];
+      dmma(c0v, c1v, -xa[0], xb[0]);
+      dmma(c0v, c1v, -xa[4], xb[4]);
+      cp[0] = c0v; cp[1] = c1v;
     }
     __syncthreads();
   }
-  if (tid < NB) sm[tid * PLD + tid] = dg[tid];
-  __syncthreads();
 
-  // ---- write L_kk (lower part, valid rows) ----
+  // ---- write L_kk (lower part, valid rows); clear the strict upper triangle in shared memory ----
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int i = idx >> 7, c = idx & 127;
-    if (i < nv && c <= i) K[(r0 + i) * ldk + r0 + c] = sm[i * PLD + c];
+    if (c <= i) { if (i < nv) K[(r0 + i) * ldk + r0 + c] = sm[i * PLD + c]; }
+    else sm[i * PLD + c] = 0.0;
   }
   __syncthreads();
-
-  // ---- inverse, level 0: the eight 16x16 diagonal sub-blocks, one thread per column ----
-  {
-    double x[16];
-    const int bb = (tid >> 4) * 16, jj = tid & 15;
-    if (tid < NB) {
-      const double* Lb = sm + bb * PLD + bb;
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        double s = (i == jj) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < i; k++) s = fma(-Lb[i * PLD + k], x[k], s);
-        x[i] = (i < jj) ? 0.0 : s / Lb[i * PLD + i];
-      }
-    }
-    __syncthreads();
-    if (tid < NB) {
-#pragma unroll
-      for (int i = 0; i < 16; i++) sm[(bb + i) * PLD + bb + jj] = x[i];
-    }
-    __syncthreads();
+  // ---- inverse: 8x8 diagonal inverses in place, then levels 8 -> 16 -> 32 -> 64 ----
+  for (int idx = tid; idx < 16 * 64; idx += 256) {
+    const int p = idx >> 6, i = (idx >> 3) & 7, j = idx & 7;
+    sm[(8 * p + i) * PLD + 8 * p + j] = inv8[idx];
   }
-  // ---- levels 16 -> 32 -> 64: X21 = -X22 L21 X11 ----
-  inv_level<16, 2, 2>(sm, tid);
-  inv_level<32, 2, 4>(sm, tid);
-  inv_level<64, 4, 4>(sm, tid);
+  __syncthreads();
+  inv_level_dmma<8>(sm, warp, lane);
+  inv_level_dmma<16>(sm, warp, lane);
+  inv_level_dmma<32>(sm, warp, lane);
+  inv_level_dmma<64>(sm, warp, lane);
 
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int i = idx >> 7, c = idx & 127;
@@ -228,7 +309,7 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
     a.c_rows_end = N; a.c_cols_end = (long long)(k + 1) * NB;
     a.epi = EPI_STORE;
     a.batch_a_rows = batch_rows; a.batch_b_rows = (long long)nblk * NB; a.batch_c_rows = batch_rows;
-    return launch_gemm(h, mapK, mapInv, a, batch, st);
+    return launch_gemm(h, mapK, mapInv, mapK, a, batch, st);
   };
   // trailing update of step k restricted to tile columns [jlo, jhi) (block indices), rows >= column
   auto update = [&](int k, int jlo, int jhi, cudaStream_t st) -> int {
@@ -246,7 +327,8 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
     }
     a.a_row0 = jlo * NB; a.b_row0 = jlo * NB;
     a.c_row0 = (long long)jlo * NB; a.c_col0 = (long long)jlo * NB;
-    return launch_gemm(h, mapK, mapK, a, batch, st);
+    a.max_tiles_per_cta = lookahead ? 8 : 16;
+    return launch_gemm(h, mapK, mapK, mapK, a, batch, st);
   };
 
   if (!lookahead) {

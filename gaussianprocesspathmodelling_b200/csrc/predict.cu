@@ -32,10 +32,11 @@ static long long chunk_rows(int sm_count, long long N, long long M, size_t ws_by
   const long long per_row = npad * 8 + 8;
   const long long cap_bytes = ws_bytes ? (long long)ws_bytes : (16ll << 30);
   long long rows = cap_bytes / per_row / NB * NB;
-  const long long wave = (long long)sm_count * NB;
-  if (rows >= wave) rows = rows / wave * wave;
   const long long need = round_up(M, NB);
-  return rows < need ? rows : need;
+  if (rows >= need) return need;                       // everything fits: one chunk
+  const long long wave = (long long)sm_count * NB;     // otherwise whole waves per chunk
+  if (rows >= wave) rows = rows / wave * wave;
+  return rows;
 }
 
 }  // namespace gpm
@@ -105,10 +106,10 @@ extern "C" int gpm_predict(gpm_handle_t handle, const double* X, int64_t N, int3
       a.c_rows_end = mc; a.c_cols_end = (long long)(k + 1) * NB;
       if (k > 0) {                       // W[:,k] -= W[:,0:k] L[k,0:k]^T
         a.a_col0 = 0; a.b_col0 = 0; a.klen = k * NB; a.epi = EPI_SUB; a.rowsq = nullptr;
-        if ((rc = launch_gemm(h, mapW, mapL, a, 1, st))) return rc;
+        if ((rc = launch_gemm(h, mapW, mapL, mapW, a, 1, st))) return rc;
       }
       a.a_col0 = k * NB; a.b_col0 = 0; a.klen = NB; a.epi = EPI_STORE; a.rowsq = rowsq;   // W[:,k] *= inv(L_kk)^T
-      if ((rc = launch_gemm(h, mapW, mapInv, a, 1, st))) return rc;
+      if ((rc = launch_gemm(h, mapW, mapInv, mapW, a, 1, st))) return rc;
     }
     var_finalize_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, st>>>(rowsq, mc, base, var + c0);
     GPM_LAUNCH_CHECK();

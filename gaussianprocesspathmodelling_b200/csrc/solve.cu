@@ -176,6 +176,7 @@ int solve_blocked(const double* L, long long N, long long ldl, const double* inv
     dim3 grid(k == nblk ? 1 : k, batch);
     bwd_step_kernel<<<grid, 256, 0, stream>>>(L, ldl, N, invD, alpha, R, k, nblk, batch_l, batch_inv, batch_z);
   }
+  count_launch(2 * nblk - 1);
   GPM_LAUNCH_CHECK();
   return 0;
 }

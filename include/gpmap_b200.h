@@ -62,6 +62,7 @@ const char* gpm_last_error(void);                     /* thread-local text of th
 int         gpm_create(gpm_handle_t* handle, int device);
 int         gpm_destroy(gpm_handle_t handle);
 int         gpm_sm_count(gpm_handle_t handle);
+long long   gpm_launch_count(void);                   /* kernels launched by this library so far (process-wide) */
 
 /* Step 1.  K = k(X,X) + noise_var*I.  Replaces  cdist(X/l, X/l,'sqeuclidean') -> np.exp -> +sigma^2 I.
  * X: N x D row-major (ldx = D).  K: N x N, leading dimension ldk. */
