@@ -66,6 +66,9 @@ struct gpm_handle_impl {
   cudaEvent_t* ev;                  // event pool (cudaEventDisableTiming)
   int n_ev;
   PFN_cuTensorMapEncodeTiled_v12000 encode;
+  int* flags;                       // 2 x n_flags device ints: block-published flags of the chained solves
+  int n_flags;
+  int epoch;                        // flag value of the current solve (monotonic, so flags need no clearing)
 };
 
 // 2-D row-major float64 tensor map with a [rows_box x 16] box and 128-byte swizzle.

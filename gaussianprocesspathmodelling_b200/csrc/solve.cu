@@ -5,6 +5,8 @@
 //                              finishes  z_i = inv(L_ii) y_i.
 // Backward (k = nblk .. 1):    every column block j < k does  z_j -= L_kj^T a_k ; block j = k-1
 //                              then finishes  a_j = inv(L_jj)^T z_j.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gpm {
@@ -163,6 +165,153 @@ lml_kernel(const double* __restrict__ L, long long ldl, long long N, const doubl
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-matrix path: one cooperative launch per direction.  CTA c owns block rows c, c+G, ... and
+// sweeps the 128x128 tiles of its block row (forward) / block column (backward) as the solution
+// blocks it depends on are published by their owners (release/acquire flags in global memory; the
+// flag value is the call's epoch so the arrays never need clearing).  L is streamed from HBM once
+// per direction with 128 KB in flight per CTA; the critical path is one flag hand-off per block.
+// ------------------------------------------------------------------------------------------------
+constexpr int CH_THREADS = 512;
+constexpr int ILD = NB + 1;
+constexpr int CHAIN_SMEM = (NB * ILD + NB * RMAX + 4 * NB * RMAX) * 8;
+
+__device__ __forceinline__ void flag_wait(const int* f, int epoch) {
+  int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  } while (v != epoch);
+}
+__device__ __forceinline__ void flag_set(int* f, int epoch) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(CH_THREADS, 1)
+solve_chain_kernel(const double* __restrict__ L, long long ldl, long long N, const double* __restrict__ invD,
+                   double* z, int R, int nblk, int* flags, int epoch) {
+  extern __shared__ double csm[];
+  double* sinv = csm;                       // [128][ILD]  inverse of this block's diagonal block
+  double* zs = sinv + NB * ILD;             // [128][RMAX] the dependency block just received
+  double* part = zs + NB * RMAX;            // [4][128][RMAX] partial sums of the four quarters
+  const int tid = threadIdx.x;
+  const int e = tid & 127, qd = tid >> 7;   // element (row fwd / column bwd) and quarter of the tile
+  const int G = gridDim.x;
+
+  for (int it = blockIdx.x; it < nblk; it += G) {
+    const int i = BWD ? nblk - 1 - it : it;                 // block owned in this iteration
+    const long long i0 = (long long)i * NB;
+    // stage inv(L_ii) (off the critical path)
+    const double* Di = invD + (long long)i * NB * NB;
+    for (int idx = tid; idx < NB * NB; idx += CH_THREADS) sinv[(idx >> 7) * ILD + (idx & 127)] = Di[idx];
+    double acc[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; r++) acc[r] = 0.0;
+
+    const int ndep = BWD ? nblk - 1 - i : i;
+    for (int dd = 0; dd < ndep; dd++) {
+      const int j = BWD ? nblk - 1 - dd : dd;               // dependency block, in publication order
+      const long long j0 = (long long)j * NB;
+      // issue this tile's loads before waiting for the dependency: they do not depend on it
+      double seg[32];
+      if (!BWD) {                                            // row i0+e, columns j0 + 32 qd .. +32
+        const long long gr = i0 + e;
+        const double2* src = reinterpret_cast<const double2*>(L + gr * ldl + j0 + 32 * qd);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          double2 v = (gr < N) ? __ldcs(src + c) : make_double2(0.0, 0.0);
+          seg[2 * c] = v.x; seg[2 * c + 1] = v.y;
+        }
+      } else {                                               // column i0+e, rows j0 + 32 qd .. +32
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+          const long long gr = j0 + 32 * qd + r;
+          seg[r] = (gr < N) ? __ldcs(L + gr * ldl + i0 + e) : 0.0;
+        }
+      }
+      if (tid == 0) flag_wait(flags + j, epoch);
+      __syncthreads();
+      for (int idx = tid; idx < NB * R; idx += CH_THREADS) {
+        const long long gr = j0 + idx / R;
+        zs[(idx / R) * RMAX + idx % R] = (gr < N) ? __ldcg(z + j0 * R + idx) : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 32; c++) {
+#pragma unroll
+        for (int r = 0; r < RMAX; r++) if (r < R) acc[r] = fma(seg[c], zs[(32 * qd + c) * RMAX + r], acc[r]);
+      }
+    }
+    // combine the quarters: y = rhs - sum
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RMAX; r++) if (r < R) part[(qd * NB + e) * RMAX + r] = acc[r];
+    __syncthreads();
+    if (tid < NB) {
+      const long long gr = i0 + tid;
+#pragma unroll
+      for (int r = 0; r < RMAX; r++) {
+        if (r < R) {
+          const double s = (part[(0 * NB + tid) * RMAX + r] + part[(1 * NB + tid) * RMAX + r]) +
+                           (part[(2 * NB + tid) * RMAX + r] + part[(3 * NB + tid) * RMAX + r]);
+          zs[tid * RMAX + r] = (gr < N) ? z[gr * R + r] - s : 0.0;
+        }
+      }
+    }
+    __syncthreads();
+    // multiply by inv(L_ii) (forward) or inv(L_ii)^T (backward) from shared memory
+#pragma unroll
+    for (int r = 0; r < RMAX; r++) acc[r] = 0.0;
+#pragma unroll 8
+    for (int c = 0; c < 32; c++) {
+      const int k = 32 * qd + c;
+      const double d = BWD ? sinv[k * ILD + e] : sinv[e * ILD + k];
+#pragma unroll
+      for (int r = 0; r < RMAX; r++) if (r < R) acc[r] = fma(d, zs[k * RMAX + r], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < RMAX; r++) if (r < R) part[(qd * NB + e) * RMAX + r] = acc[r];
+    __syncthreads();
+    if (tid < NB) {
+      const long long gr = i0 + tid;
+      if (gr < N) {
+#pragma unroll
+        for (int r = 0; r < RMAX; r++) {
+          if (r < R)
+            z[gr * R + r] = (part[(0 * NB + tid) * RMAX + r] + part[(1 * NB + tid) * RMAX + r]) +
+                            (part[(2 * NB + tid) * RMAX + r] + part[(3 * NB + tid) * RMAX + r]);
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) flag_set(flags + i, epoch);
+  }
+}
+
+int solve_chain(gpm_handle_impl* h, const double* L, long long N, long long ldl, const double* invD,
+                double* alpha, int R, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    GPM_CUDA(cudaFuncSetAttribute(solve_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
+    GPM_CUDA(cudaFuncSetAttribute(solve_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
+    attr_set = true;
+  }
+  int nblk = (int)((N + NB - 1) / NB);
+  if (nblk > h->n_flags) { set_error("solve: N too large for the handle's flag arrays"); return 997; }
+  int grid = nblk < h->sm_count ? nblk : h->sm_count;
+  for (int dir = 0; dir < 2; dir++) {
+    int epoch = ++h->epoch;
+    int* flags = h->flags + dir * h->n_flags;
+    void* args[] = {(void*)&L, (void*)&ldl, (void*)&N, (void*)&invD, (void*)&alpha, (void*)&R, (void*)&nblk,
+                    (void*)&flags, (void*)&epoch};
+    const void* fn = dir == 0 ? (const void*)solve_chain_kernel<false> : (const void*)solve_chain_kernel<true>;
+    GPM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(CH_THREADS), args, CHAIN_SMEM, stream));
+    count_launch(1);
+  }
+  return 0;
+}
+
 // alpha (N x R per matrix) must already hold a copy of Y; solved in place.
 int solve_blocked(const double* L, long long N, long long ldl, const double* invD, double* alpha, int R,
                   int batch, long long batch_l, long long batch_inv, long long batch_z,
@@ -204,7 +353,10 @@ extern "C" int gpm_solve_lml(gpm_handle_t h, const double* L, int64_t N, int64_t
   GPM_ARG(alpha != nullptr && alpha != Y, 8);
   cudaStream_t st = (cudaStream_t)stream;
   GPM_CUDA(cudaMemcpyAsync(alpha, Y, (size_t)N * R * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  int rc = solve_blocked(L, N, ldl, reinterpret_cast<const double*>(potrf_ws), alpha, R, 1, 0, 0, 0, st);
+  gpm_handle_impl* hi = reinterpret_cast<gpm_handle_impl*>(h);
+  int rc = getenv("GPM_SOLVE_STEPS")
+               ? solve_blocked(L, N, ldl, reinterpret_cast<const double*>(potrf_ws), alpha, R, 1, 0, 0, 0, st)
+               : solve_chain(hi, L, N, ldl, reinterpret_cast<const double*>(potrf_ws), alpha, R, st);
   if (rc) return rc;
   if (lml) return launch_lml(L, N, ldl, Y, alpha, R, lml, 1, 0, 0, st);
   return 0;
