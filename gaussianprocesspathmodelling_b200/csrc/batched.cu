@@ -11,6 +11,9 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
                   int batch, long long batch_rows, cudaStream_t s0);
 int solve_blocked(const double* L, long long N, long long ldl, const double* invD, double* alpha, int R,
                   int batch, long long batch_l, long long batch_inv, long long batch_z, cudaStream_t stream);
+int solve_paths(const double* L, long long N, long long ldl, const double* invD, const double* Y,
+                double* alpha, double* lml, int R, int batch, long long batch_l, long long batch_inv,
+                long long batch_y, cudaStream_t stream);
 int launch_lml(const double* L, long long N, long long ldl, const double* Y, const double* alpha, int R,
                double* lml, int batch, long long batch_l, long long batch_y, cudaStream_t stream);
 
@@ -50,6 +53,8 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
   int rc;
   if ((rc = launch_cov(Xb, N, D, th, Kb, np, 1, (int)B, N * D, np * np, st))) return rc;
   if ((rc = potrf_blocked(h, Kb, N, np, invD, info, (int)B, np, st))) return rc;
+  rc = solve_paths(Kb, N, np, invD, Yb, alpha, lml, R, (int)B, np * np, (long long)nblk * NB * NB, N * R, st);
+  if (rc >= 0) return rc;
   GPM_CUDA(cudaMemcpyAsync(alpha, Yb, (size_t)B * N * R * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if ((rc = solve_blocked(Kb, N, np, invD, alpha, R, (int)B, np * np, (long long)nblk * NB * NB, N * R, st))) return rc;
   if (lml) return launch_lml(Kb, N, np, Yb, alpha, R, lml, (int)B, np * np, N * R, st);

@@ -15,76 +15,68 @@
 
 namespace gpm {
 
-constexpr int PLD = NB + 1;   // padded smem pitch (doubles) of the 128x128 block
-constexpr int XLD = 12;       // pitch of the 8-column panel staging buffer (conflict-free DMMA fragment reads)
-constexpr int POTF2_SMEM = (NB * PLD + NB * XLD + 16 * 64) * 8;
+constexpr int PLD = NB + 4;   // smem pitch (doubles) of the 128x128 block: = 4 mod 16 makes DMMA A/B fragment reads
+                              // conflict-free and keeps rows 16-byte aligned for 128-bit C-fragment accesses
+constexpr int XLD = 12;
+constexpr int P2_THREADS = 512, P2_WARPS = P2_THREADS / 32;   // potf2 CTA: latency-bound, so more warps help       // pitch of the 8-column panel staging buffer (conflict-free DMMA fragment reads)
+constexpr int POTF2_SMEM = (NB * PLD + NB * XLD + 64 + NB) * 8;
 
-// One 8x8 lower-triangular factor + its inverse, entirely in one thread's registers.
-// a: packed lower (row-major, a[i*(i+1)/2 + j]); on exit a holds L, x holds inv(L) (same packing).
+// 8x8 lower Cholesky in one thread's registers (right-looking, so the serial chain per column is
+// rsqrt -> scale -> one FMA).  a: packed lower (a[i*(i+1)/2 + j]); on exit a holds L and r[j] = 1/L_jj.
+// Every loop has constant bounds with compile-time-foldable guards so the arrays stay in registers.
 // Returns the 1-based index of the first non-positive pivot (0 if none).
-__device__ __forceinline__ int chol8_inv(double (&a)[36], double (&x)[36]) {
-  // every loop has constant bounds 0..7 with compile-time-foldable guards, so that full unrolling
-  // keeps both arrays in registers
-  double r[8];
+__device__ __forceinline__ int chol8(double (&a)[36], double (&r)[8]) {
   int bad = 0;
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     double d = a[j * (j + 1) / 2 + j];
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      if (k < j) d = fma(-a[j * (j + 1) / 2 + k], a[j * (j + 1) / 2 + k], d);
     if (!(d > 0.0) || !(d < 1.0e300)) { if (!bad) bad = j + 1; d = 1.0; }
-    const double ljj = sqrt(d);
-    r[j] = 1.0 / ljj;
-    a[j * (j + 1) / 2 + j] = ljj;
+    r[j] = rsqrt(d);                       // 1 ulp; sqrt + divide would cost ~5x the latency on this serial path
+    a[j * (j + 1) / 2 + j] = d * r[j];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      if (i > j) {
-        double v = a[i * (i + 1) / 2 + j];
+    for (int i = 0; i < 8; i++)
+      if (i > j) a[i * (i + 1) / 2 + j] *= r[j];
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-          if (k < j) v = fma(-a[i * (i + 1) / 2 + k], a[j * (j + 1) / 2 + k], v);
-        a[i * (i + 1) / 2 + j] = v * r[j];
-      }
-    }
-  }
+    for (int i = 0; i < 8; i++)
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    x[j * (j + 1) / 2 + j] = r[j];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      if (i > j) {
-        double v = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-          if (k >= j && k < i) v = fma(a[i * (i + 1) / 2 + k], x[k * (k + 1) / 2 + j], v);
-        x[i * (i + 1) / 2 + j] = -v * r[i];
-      }
-    }
+      for (int c = 0; c < 8; c++)
+        if (i > j && c > j && c <= i)
+          a[i * (i + 1) / 2 + c] = fma(-a[i * (i + 1) / 2 + j], a[c * (c + 1) / 2 + j], a[i * (i + 1) / 2 + c]);
   }
   return bad;
 }
 
 // One level of the recursive-doubling inverse on DMMA tiles:  X21 = -X22 * (L21 * X11)  for all
 // 64/S pairs of SxS diagonal blocks (X11, X22 already inverted in place, upper parts zero).
+// The contraction loop is outermost so that a warp keeps PER_WARP independent DMMA chains in flight.
 template <int S>
 __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
   constexpr int TB = S / 8;                 // 8x8 tiles per block edge
   constexpr int TILES = (NB / (2 * S)) * TB * TB;
-  constexpr int PER_WARP = (TILES + 7) / 8;
+  constexpr int PER_WARP = (TILES + P2_WARPS - 1) / P2_WARPS;
   const int g = lane >> 2, q = lane & 3;
   double c0[PER_WARP], c1[PER_WARP];
-  // phase 1: T = L21 * X11   (X11 lower: contraction blocks kb >= b)
+  int ra[PER_WARP], cb[PER_WARP], ta[PER_WARP], tb[PER_WARP], o1s[PER_WARP];
+  bool ok[PER_WARP];
 #pragma unroll
   for (int e = 0; e < PER_WARP; e++) {
-    const int t = warp + 8 * e;
+    const int t = warp + P2_WARPS * e;
+    ok[e] = t < TILES;
+    const int tt = ok[e] ? t : 0;
+    const int pair = tt / (TB * TB);
+    ta[e] = (tt / TB) % TB; tb[e] = tt % TB;
+    o1s[e] = pair * 2 * S;
+    ra[e] = o1s[e] + S + 8 * ta[e] + g;     // output row (in the 2-block), this lane
+    cb[e] = o1s[e] + 8 * tb[e];             // output column base
     c0[e] = c1[e] = 0.0;
-    if (t < TILES) {
-      const int pair = t / (TB * TB), a = (t / TB) % TB, b = t % TB;
-      const int o1 = pair * 2 * S, o2 = o1 + S;
-      for (int k0 = 8 * b; k0 < S; k0 += 4) {
-        const double af = sm[(o2 + 8 * a + g) * PLD + o1 + k0 + q];
-        const double bf = sm[(o1 + k0 + q) * PLD + o1 + 8 * b + g];
+  }
+  // phase 1: T = L21 * X11   (X11 lower: contraction k >= 8 b)
+  for (int k0 = 0; k0 < S; k0 += 4) {
+#pragma unroll
+    for (int e = 0; e < PER_WARP; e++) {
+      if (ok[e] && k0 >= 8 * tb[e]) {
+        const double af = sm[ra[e] * PLD + o1s[e] + k0 + q];
+        const double bf = sm[(o1s[e] + k0 + q) * PLD + cb[e] + g];
         dmma(c0[e], c1[e], af, bf);
       }
     }
@@ -92,152 +84,222 @@ __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < PER_WARP; e++) {
-    const int t = warp + 8 * e;
-    if (t < TILES) {
-      const int pair = t / (TB * TB), a = (t / TB) % TB, b = t % TB;
-      const int o1 = pair * 2 * S, o2 = o1 + S;
-      double* dst = sm + (o2 + 8 * a + g) * PLD + o1 + 8 * b + 2 * q;
-      dst[0] = c0[e]; dst[1] = c1[e];
-    }
+    if (ok[e]) *reinterpret_cast<double2*>(sm + ra[e] * PLD + cb[e] + 2 * q) = make_double2(c0[e], c1[e]);
+    c0[e] = c1[e] = 0.0;
   }
   __syncthreads();
-  // phase 2: X21 = -X22 * T   (X22 lower: contraction blocks kb <= a)
+  // phase 2: X21 = -X22 * T   (X22 lower: contraction k < 8 a + 8)
+  for (int k0 = 0; k0 < S; k0 += 4) {
 #pragma unroll
-  for (int e = 0; e < PER_WARP; e++) {
-    const int t = warp + 8 * e;
-    c0[e] = c1[e] = 0.0;
-    if (t < TILES) {
-      const int pair = t / (TB * TB), a = (t / TB) % TB, b = t % TB;
-      const int o1 = pair * 2 * S, o2 = o1 + S;
-      for (int k0 = 0; k0 < 8 * a + 8; k0 += 4) {
-        const double af = -sm[(o2 + 8 * a + g) * PLD + o2 + k0 + q];
-        const double bf = sm[(o2 + k0 + q) * PLD + o1 + 8 * b + g];
+    for (int e = 0; e < PER_WARP; e++) {
+      if (ok[e] && k0 < 8 * ta[e] + 8) {
+        const double af = -sm[ra[e] * PLD + o1s[e] + S + k0 + q];
+        const double bf = sm[(o1s[e] + S + k0 + q) * PLD + cb[e] + g];
         dmma(c0[e], c1[e], af, bf);
       }
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int e = 0; e < PER_WARP; e++) {
-    const int t = warp + 8 * e;
-    if (t < TILES) {
-      const int pair = t / (TB * TB), a = (t / TB) % TB, b = t % TB;
-      const int o1 = pair * 2 * S, o2 = o1 + S;
-      double* dst = sm + (o2 + 8 * a + g) * PLD + o1 + 8 * b + 2 * q;
-      dst[0] = c0[e]; dst[1] = c1[e];
-    }
-  }
+  for (int e = 0; e < PER_WARP; e++)
+    if (ok[e]) *reinterpret_cast<double2*>(sm + ra[e] * PLD + cb[e] + 2 * q) = make_double2(c0[e], c1[e]);
   __syncthreads();
 }
+
+#ifdef GPM_POTF2_TIMING
+#define PT_DECL long long pt_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_c = clock64();
+#define PT_MARK(i) { double d_ = *(volatile double*)sm; long long n_; \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(n_) : "l"(__double_as_longlong(d_)) : "memory"); \
+    pt_t[i] += n_ - pt_c; pt_c = n_; }
+#define PT_DUMP if (blockIdx.x == 0 && threadIdx.x == 0 && kblk == 0) \
+    printf("potf2 cycles: load %lld | diag8 %lld | panel %lld | trail %lld | storeL %lld | inv %lld | storeI %lld\n", \
+           pt_t[0], pt_t[1], pt_t[2], pt_t[3], pt_t[4], pt_t[5], pt_t[6]);
+#else
+#define PT_DECL
+#define PT_MARK(i)
+#define PT_DUMP
+#endif
 
 // Factor diagonal block kblk of K in shared memory, write L_kk back and inv(L_kk) to invD.
 // Rows/columns beyond N are padded with the identity.  blockIdx.x = batch index.
 //
-// Right-looking over sixteen 8-column panels: (1) one thread factors and inverts the 8x8 diagonal
-// block in registers, (2) one thread per row solves the panel against it, (3) all warps apply the
-// rank-8 update to the trailing 8x8 tiles with two DMMA.8x8x4 each.  The 128x128 inverse is then
-// assembled from the 8x8 inverses by recursive doubling, also on DMMA tiles.
-__global__ void __launch_bounds__(256, 1)
+// Right-looking over sixteen 8-column panels: (1) one thread factors the 8x8 diagonal block in
+// registers, (2) one thread per row forward-substitutes the panel against it, (3) all warps apply
+// the rank-8 update to the trailing 8x8 tiles with two DMMA.8x8x4 each, four tiles in flight per warp
+// (a dependent DMMA pair costs ~290 cycles).  The 128x128 inverse is then assembled from the 8x8
+// diagonal inverses by recursive doubling, also on DMMA tiles.
+__global__ void __launch_bounds__(P2_THREADS, 1)
 potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, double* __restrict__ invD,
                  int* __restrict__ info, long long batch_k, long long batch_inv) {
   extern __shared__ double sm[];
   double* xp = sm + NB * PLD;          // [128][XLD] current panel
-  double* inv8 = xp + NB * XLD;        // [16][64]  inverses of the 8x8 diagonal blocks (full, zero upper)
+  double* l8 = xp + NB * XLD;          // [36] current 8x8 factor (packed lower)
+  double* rd = l8 + 64;                // [128] reciprocals of the diagonal of L
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   K += blockIdx.x * batch_k;
   invD += blockIdx.x * batch_inv + (long long)kblk * NB * NB;
   info += blockIdx.x;
   const long long r0 = (long long)kblk * NB;
   const int nv = (int)((N - r0) < NB ? (N - r0) : NB);
+  PT_DECL
 
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int i = idx >> 7, c = idx & 127;
-    double v;
-    if (i < nv && c < nv) v = (c <= i) ? K[(r0 + i) * ldk + r0 + c] : 0.0;
-    else v = (i == c) ? 1.0 : 0.0;
-    sm[i * PLD + c] = v;
+  // load (16 independent loads in flight per thread)
+  for (int u0 = 0; u0 < NB * NB / P2_THREADS; u0 += 16) {
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 7, c = idx & 127;
+      const bool in = (i < nv) && (c <= i);
+      v[u] = in ? K[(r0 + i) * ldk + r0 + c] : ((i == c && i >= nv) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int idx = tid + P2_THREADS * (u0 + u);
+      sm[(idx >> 7) * PLD + (idx & 127)] = v[u];
+    }
   }
   __syncthreads();
+  PT_MARK(0)
 
   const int g = lane >> 2, q = lane & 3;
   for (int p = 0; p < 16; p++) {
     const int c0 = 8 * p;
-    // (1) 8x8 diagonal block: factor + invert in one thread
+    // (1) 8x8 diagonal block: factor in one thread
     if (tid == 0) {
-      double a[36], x[36];
+      double a[36], r[8];
 #pragma unroll
       for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j <= i; j++) a[i * (i + 1) / 2 + j] = sm[(c0 + i) * PLD + c0 + j];
-      const int bad = chol8_inv(a, x);
+      const int bad = chol8(a, r);
       if (bad && c0 + bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + c0 + bad));
 #pragma unroll
-      for (int i = 0; i < 8; i++)
+      for (int i = 0; i < 8; i++) {
+        rd[c0 + i] = r[i];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          if (j <= i) sm[(c0 + i) * PLD + c0 + j] = a[i * (i + 1) / 2 + j];
-          inv8[p * 64 + i * 8 + j] = (j <= i) ? x[i * (i + 1) / 2 + j] : 0.0;
+        for (int j = 0; j <= i; j++) {
+          sm[(c0 + i) * PLD + c0 + j] = a[i * (i + 1) / 2 + j];
+          l8[i * (i + 1) / 2 + j] = a[i * (i + 1) / 2 + j];
         }
+      }
     }
     __syncthreads();
-    // (2) panel solve: X[i, 0:8] = A[i, c0:c0+8] * inv(L8)^T, one thread per row below the block
+    PT_MARK(1)
+    // (2) panel solve by forward substitution, one thread per row below the block:
+    //     x_c = (a_c - sum_{k<c} x_k L8[c][k]) / L8[c][c]
     if (tid < NB && tid >= c0 + 8) {
-      double a[8], x[8];
+      double x[8];
       double* row = sm + tid * PLD + c0;
 #pragma unroll
-      for (int k = 0; k < 8; k++) a[k] = row[k];
-#pragma unroll
       for (int c = 0; c < 8; c++) {
-        double v = 0.0;
+        double v = row[c];
 #pragma unroll
-        for (int k = 0; k <= c; k++) v = fma(a[k], inv8[p * 64 + c * 8 + k], v);
-        x[c] = v;
+        for (int k = 0; k < 8; k++)
+          if (k < c) v = fma(-x[k], l8[c * (c + 1) / 2 + k], v);
+        x[c] = v * rd[c0 + c];
       }
 #pragma unroll
       for (int c = 0; c < 8; c++) { row[c] = x[c]; xp[tid * XLD + c] = x[c]; }
     }
     __syncthreads();
-    // (3) trailing update on 8x8 tiles: C[ti][tj] -= X_ti X_tj^T, two DMMAs per tile
+    PT_MARK(2)
+    // (3) trailing update on 8x8 tiles: C[ti][tj] -= X_ti X_tj^T; four independent tiles per iteration
     const int nt = 15 - p, rb = c0 + 8;
     const int ntiles = nt * (nt + 1) / 2;
-    for (int e = warp; e < ntiles; e += 8) {
-      int ti = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-      while ((ti + 1) * (ti + 2) / 2 <= e) ti++;
-      while (ti * (ti + 1) / 2 > e) ti--;
-      const int tj = e - ti * (ti + 1) / 2;
-      const double* xa = xp + (rb + 8 * ti + g) * XLD + q;
-      const double* xb = xp + (rb + 8 * tj + g) * XLD + q;
-      double* cp = sm + (rb + 8 * ti + g) * PLD + rb + 8 * tj + 2 * q;
-      double c0v = cp[0], c1v = cp[1];
-      dmma(c0v, c1v, -xa[0], xb[0]);
-      dmma(c0v, c1v, -xa[4], xb[4]);
-      cp[0] = c0v; cp[1] = c1v;
+    // balanced static schedule: tile-rows a and b = nt-1-a together hold nt+1 tiles; warps 2a and 2a+1
+    // each take half of that run, so no warp does more than ceil((nt+1)/2) tiles and there is no
+    // per-tile index search.  The A fragment (rows of tile-row ti) stays in registers along a row.
+    {
+      const int a_row = warp >> 1, b_row = nt - 1 - a_row;
+      if (a_row <= b_row) {
+        const int na = a_row + 1;
+        const int total = (a_row == b_row) ? na : nt + 1;
+        const int halfn = (total + 1) >> 1;
+        const int pos0 = (warp & 1) * halfn;
+        const int pos1 = min(total, pos0 + halfn);
+        // DMMA.8x8x4 latency is ~130 cycles: keep four independent DMMAs in flight (two tiles, each
+        // with its two k-halves in separate accumulators) instead of dependent pairs.
+        for (int pos = pos0; pos < pos1; pos += 2) {
+          const bool two = pos + 1 < pos1;
+          const int pb_ = two ? pos + 1 : pos;
+          const int ti0 = pos < na ? a_row : b_row, tj0 = pos < na ? pos : pos - na;
+          const int ti1 = pb_ < na ? a_row : b_row, tj1 = pb_ < na ? pb_ : pb_ - na;
+          const double* xa_0 = xp + (rb + 8 * ti0 + g) * XLD + q;
+          const double* xa_1 = xp + (rb + 8 * ti1 + g) * XLD + q;
+          const double* xb_0 = xp + (rb + 8 * tj0 + g) * XLD + q;
+          const double* xb_1 = xp + (rb + 8 * tj1 + g) * XLD + q;
+          double2* cp0 = reinterpret_cast<double2*>(sm + (rb + 8 * ti0 + g) * PLD + rb + 8 * tj0 + 2 * q);
+          double2* cp1 = reinterpret_cast<double2*>(sm + (rb + 8 * ti1 + g) * PLD + rb + 8 * tj1 + 2 * q);
+          const double a00 = -xa_0[0], a01 = -xa_0[4], a10 = -xa_1[0], a11 = -xa_1[4];
+          const double b00 = xb_0[0], b01 = xb_0[4], b10 = xb_1[0], b11 = xb_1[4];
+          double2 c0v = *cp0, c1v = *cp1;
+          double2 p0 = make_double2(0.0, 0.0), p1 = make_double2(0.0, 0.0);
+          dmma(c0v.x, c0v.y, a00, b00);
+          dmma(p0.x, p0.y, a01, b01);
+          dmma(c1v.x, c1v.y, a10, b10);
+          dmma(p1.x, p1.y, a11, b11);
+          c0v.x += p0.x; c0v.y += p0.y;
+          *cp0 = c0v;
+          if (two) { c1v.x += p1.x; c1v.y += p1.y; *cp1 = c1v; }
+        }
+      }
     }
     __syncthreads();
+    PT_MARK(3)
   }
 
-  // ---- write L_kk (lower part, valid rows); clear the strict upper triangle in shared memory ----
-  for (int idx = tid; idx < NB * NB; idx += 256) {
+  // ---- write L_kk (lower part, valid rows) ----
+  for (int u0 = 0; u0 < NB * NB / P2_THREADS; u0 += 16) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 7, c = idx & 127;
+      if (c <= i && i < nv) K[(r0 + i) * ldk + r0 + c] = sm[i * PLD + c];
+    }
+  }
+  // ---- inverse, level 0: the sixteen 8x8 diagonal blocks, one thread per column ----
+  double xcol[8];
+  {
+    const int pb = (tid >> 3) * 8, j = tid & 7;
+    if (tid < NB) {
+      const double* Lb = sm + pb * PLD + pb;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (k < i) v = fma(Lb[i * PLD + k], (k >= j) ? xcol[k] : 0.0, v);
+        xcol[i] = (i < j) ? 0.0 : ((i == j) ? rd[pb + i] : -v * rd[pb + i]);
+      }
+    }
+  }
+  __syncthreads();
+  // clear the strict upper triangle (the diagonal-tile updates wrote symmetric garbage there)
+  for (int idx = tid; idx < NB * NB; idx += P2_THREADS) {
     const int i = idx >> 7, c = idx & 127;
-    if (c <= i) { if (i < nv) K[(r0 + i) * ldk + r0 + c] = sm[i * PLD + c]; }
-    else sm[i * PLD + c] = 0.0;
+    if (c > i) sm[i * PLD + c] = 0.0;
+  }
+  if (tid < NB) {
+    const int pb = (tid >> 3) * 8, j = tid & 7;
+#pragma unroll
+    for (int i = 0; i < 8; i++) sm[(pb + i) * PLD + pb + j] = xcol[i];
   }
   __syncthreads();
-  // ---- inverse: 8x8 diagonal inverses in place, then levels 8 -> 16 -> 32 -> 64 ----
-  for (int idx = tid; idx < 16 * 64; idx += 256) {
-    const int p = idx >> 6, i = (idx >> 3) & 7, j = idx & 7;
-    sm[(8 * p + i) * PLD + 8 * p + j] = inv8[idx];
-  }
-  __syncthreads();
+  PT_MARK(4)
   inv_level_dmma<8>(sm, warp, lane);
   inv_level_dmma<16>(sm, warp, lane);
   inv_level_dmma<32>(sm, warp, lane);
   inv_level_dmma<64>(sm, warp, lane);
+  PT_MARK(5)
 
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int i = idx >> 7, c = idx & 127;
-    invD[idx] = sm[i * PLD + c];
+  for (int u0 = 0; u0 < NB * NB / P2_THREADS; u0 += 16) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int idx = tid + P2_THREADS * (u0 + u);
+      invD[idx] = sm[(idx >> 7) * PLD + (idx & 127)];
+    }
   }
+  PT_MARK(6)
+  PT_DUMP
 }
 
 __global__ void zero_info_kernel(int* info, int n) {
@@ -252,7 +314,7 @@ int launch_potf2(double* K, long long ldk, long long N, int kblk, double* invD, 
     GPM_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
     attr_set = true;
   }
-  potf2_inv_kernel<<<batch, 256, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv);
+  potf2_inv_kernel<<<batch, P2_THREADS, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv);
   GPM_LAUNCH_CHECK();
   return 0;
 }

@@ -312,6 +312,168 @@ int solve_chain(gpm_handle_impl* h, const double* L, long long N, long long ldl,
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Batched path: one CTA per path runs forward + backward substitution and the LML over its own
+// factor; the whole right-hand side lives in shared memory, L and the inverted diagonal blocks are
+// streamed once per direction (128 KB in flight per CTA).  No inter-CTA dependencies.
+// ------------------------------------------------------------------------------------------------
+constexpr int SB_MAXN = 2048;
+
+__global__ void __launch_bounds__(CH_THREADS, 1)
+solve_path_kernel(const double* __restrict__ Lb, long long ldl, long long N, const double* __restrict__ invDb,
+                  const double* __restrict__ Yb, double* __restrict__ alphab, double* __restrict__ lmlb,
+                  int R, int nblk, long long batch_l, long long batch_inv, long long batch_y) {
+  extern __shared__ double psm[];
+  double* zs = psm;                                   // [nblk*128][RMAX]
+  double* part = zs + (long long)nblk * NB * RMAX;    // [4][128][RMAX]
+  double* ys = part + 4 * NB * RMAX;                  // [128][RMAX]
+  __shared__ double red[CH_THREADS / 32][RMAX + 1];
+  const double* L = Lb + blockIdx.x * batch_l;
+  const double* invD = invDb + blockIdx.x * batch_inv;
+  const double* Y = Yb + blockIdx.x * batch_y;
+  double* alpha = alphab + blockIdx.x * batch_y;
+  const int tid = threadIdx.x, e = tid & 127, qd = tid >> 7, warp = tid >> 5, lane = tid & 31;
+
+  for (int idx = tid; idx < nblk * NB * RMAX; idx += CH_THREADS) {
+    const int row = idx / RMAX, r = idx % RMAX;
+    zs[idx] = (row < N && r < R) ? Y[(long long)row * R + r] : 0.0;
+  }
+  double logdet = 0.0;
+  for (long long i = tid; i < N; i += CH_THREADS) logdet += log(L[i * ldl + i]);
+  __syncthreads();
+
+  for (int dir = 0; dir < 2; dir++) {
+    for (int it = 0; it < nblk; it++) {
+      const int i = dir ? nblk - 1 - it : it;
+      const long long i0 = (long long)i * NB;
+      double acc[RMAX];
+#pragma unroll
+      for (int r = 0; r < RMAX; r++) acc[r] = 0.0;
+      const int ndep = dir ? nblk - 1 - i : i;
+      for (int dd = 0; dd < ndep; dd++) {
+        const int j = dir ? nblk - 1 - dd : dd;
+        const long long j0 = (long long)j * NB;
+        double seg[32];
+        if (!dir) {
+          const long long gr = i0 + e;
+          const double2* src = reinterpret_cast<const double2*>(L + gr * ldl + j0 + 32 * qd);
+#pragma unroll
+          for (int c = 0; c < 16; c++) {
+            double2 v = (gr < N) ? __ldcs(src + c) : make_double2(0.0, 0.0);
+            seg[2 * c] = v.x; seg[2 * c + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 32; r++) {
+            const long long gr = j0 + 32 * qd + r;
+            seg[r] = (gr < N) ? __ldcs(L + gr * ldl + i0 + e) : 0.0;
+          }
+        }
+        const double* zj = zs + (j0 + 32 * qd) * RMAX;
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+#pragma unroll
+          for (int r = 0; r < RMAX; r++) if (r < R) acc[r] = fma(seg[c], zj[c * RMAX + r], acc[r]);
+        }
+      }
+      // diagonal-block inverse segment (issued before the reduction barriers)
+      double dseg[32];
+      {
+        const double* Di = invD + (long long)i * NB * NB;
+        if (!dir) {
+          const double2* src = reinterpret_cast<const double2*>(Di + e * NB + 32 * qd);
+#pragma unroll
+          for (int c = 0; c < 16; c++) { double2 v = __ldcs(src + c); dseg[2 * c] = v.x; dseg[2 * c + 1] = v.y; }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 32; r++) dseg[r] = __ldcs(Di + (32 * qd + r) * NB + e);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RMAX; r++) if (r < R) part[(qd * NB + e) * RMAX + r] = acc[r];
+      __syncthreads();
+      if (tid < NB) {
+#pragma unroll
+        for (int r = 0; r < RMAX; r++) {
+          if (r < R) {
+            const double sgm = (part[(0 * NB + tid) * RMAX + r] + part[(1 * NB + tid) * RMAX + r]) +
+                               (part[(2 * NB + tid) * RMAX + r] + part[(3 * NB + tid) * RMAX + r]);
+            ys[tid * RMAX + r] = zs[(i0 + tid) * RMAX + r] - sgm;
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < RMAX; r++) acc[r] = 0.0;
+#pragma unroll
+      for (int c = 0; c < 32; c++) {
+#pragma unroll
+        for (int r = 0; r < RMAX; r++) if (r < R) acc[r] = fma(dseg[c], ys[(32 * qd + c) * RMAX + r], acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < RMAX; r++) if (r < R) part[(qd * NB + e) * RMAX + r] = acc[r];
+      __syncthreads();
+      if (tid < NB) {
+#pragma unroll
+        for (int r = 0; r < RMAX; r++) {
+          if (r < R) {
+            const double v = (part[(0 * NB + tid) * RMAX + r] + part[(1 * NB + tid) * RMAX + r]) +
+                             (part[(2 * NB + tid) * RMAX + r] + part[(3 * NB + tid) * RMAX + r]);
+            zs[(i0 + tid) * RMAX + r] = (i0 + tid < N) ? v : 0.0;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // alpha out + LML
+  double acc[RMAX + 1];
+#pragma unroll
+  for (int r = 0; r < RMAX; r++) acc[r] = 0.0;
+  acc[RMAX] = logdet;
+  for (long long i = tid; i < N; i += CH_THREADS) {
+#pragma unroll
+    for (int r = 0; r < RMAX; r++) {
+      if (r < R) {
+        const double a = zs[i * RMAX + r];
+        alpha[i * R + r] = a;
+        acc[r] = fma(Y[i * R + r], a, acc[r]);
+      }
+    }
+  }
+  if (lmlb == nullptr) return;
+#pragma unroll
+  for (int r = 0; r <= RMAX; r++) acc[r] = warp_sum(acc[r]);
+  if (lane == 0) for (int r = 0; r <= RMAX; r++) red[warp][r] = acc[r];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int r = 0; r <= RMAX; r++) acc[r] = warp_sum(lane < CH_THREADS / 32 ? red[lane][r] : 0.0);
+    if (lane == 0) {
+      const double c = 0.5 * (double)N * 1.8378770664093454835606594728112;
+      for (int r = 0; r < R; r++) lmlb[blockIdx.x * R + r] = -0.5 * acc[r] - acc[RMAX] - c;
+    }
+  }
+}
+
+// returns -1 when the shape is not supported by the one-CTA-per-path kernel
+int solve_paths(const double* L, long long N, long long ldl, const double* invD, const double* Y,
+                double* alpha, double* lml, int R, int batch, long long batch_l, long long batch_inv,
+                long long batch_y, cudaStream_t stream) {
+  const int nblk = (int)((N + NB - 1) / NB);
+  if ((long long)nblk * NB > SB_MAXN) return -1;
+  const int smem = (nblk * NB * RMAX + 4 * NB * RMAX + NB * RMAX) * 8;
+  static int attr = 0;
+  if (smem > attr) {
+    GPM_CUDA(cudaFuncSetAttribute(solve_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = smem;
+  }
+  solve_path_kernel<<<batch, CH_THREADS, smem, stream>>>(L, ldl, N, invD, Y, alpha, lml, R, nblk, batch_l,
+                                                         batch_inv, batch_y);
+  GPM_LAUNCH_CHECK();
+  return 0;
+}
+
 // alpha (N x R per matrix) must already hold a copy of Y; solved in place.
 int solve_blocked(const double* L, long long N, long long ldl, const double* invD, double* alpha, int R,
                   int batch, long long batch_l, long long batch_inv, long long batch_z,
