@@ -50,6 +50,18 @@ def load_peaks():
     return peaks
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of the dominant kernel from the committed ncu capture (deep-K update launch)."""
+    try:
+        s = json.load(open(os.path.join(ROOT, "profiles", "r01_v4_ncu_gemm_summary.json")))
+        l = s["launches"][1]
+        return {"bytes_per_launch": l["dram_read_bytes"] + l["dram_write_bytes"], "launch": l["role"],
+                "algorithmic_operand_bytes": l["algorithmic_operand_bytes"], "duration_ms": l["duration_ms"],
+                "dmma_pipe_active_pct": l["dmma_pipe_active_pct"], "source": "profiles/r01_v4_ncu_gemm_summary.json"}
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------------
@@ -346,7 +358,7 @@ def run_b200(args):
     roofline = {
         "kernel": "gemm_nt_kernel (DMMA.8x8x4 + TMA) inside the blocked TRSM of the posterior variance",
         "bound": "tensor", "achieved": var_tflops, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
-        "frac": var_tflops / peaks["fp64_tflops"], "traffic": None,
+        "frac": var_tflops / peaks["fp64_tflops"], "traffic": ncu_traffic(),
         "peak_source": peaks["fp64_src"],
         "launches_per_step": int(gemm_launches), "flops_per_launch": var_flops / max(1, gemm_launches),
         "avg_launch_ms": phases["predict_var_ms"] / max(1, gemm_launches),
