@@ -11,6 +11,8 @@
 // bulk of step k's tensor-core work.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "gemm.cuh"
 
 namespace gpm {
@@ -348,7 +350,7 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
   rc = make_tmap(h, &mapInv, invD, (long long)batch * nblk * NB, NB, NB, NB);
   if (rc) return rc;
   const long long batch_k = batch_rows * ldk, batch_inv = (long long)nblk * NB * NB;
-  const bool lookahead = getenv("GPM_NO_LOOKAHEAD") == nullptr && nblk > 2;
+  const bool lookahead = getenv("GPM_NO_LOOKAHEAD") == nullptr && nblk > 2 && batch < 32;
   cudaStream_t s1 = lookahead ? h->aux : s0;
   rc = ensure_events(h, 2 * nblk + 2);
   if (rc) return rc;
@@ -373,51 +375,78 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
     a.batch_a_rows = batch_rows; a.batch_b_rows = (long long)nblk * NB; a.batch_c_rows = batch_rows;
     return launch_gemm(h, mapK, mapInv, mapK, a, batch, st);
   };
-  // trailing update of step k restricted to tile columns [jlo, jhi) (block indices), rows >= column
-  auto update = [&](int k, int jlo, int jhi, cudaStream_t st) -> int {
-    if (jlo >= jhi) return 0;
+  // trailing update with block columns [k0, k0+kw) of L (contraction length kw*NB) restricted to tile
+  // columns [jlo, jhi) (block indices), rows >= column
+  auto update = [&](int k0, int kw, int jlo, int jhi, cudaStream_t st) -> int {
+    if (jlo >= jhi || jlo >= nblk) return 0;
     GemmArgs a = {};
     a.C = K; a.ldc = ldk; a.rowsq = nullptr;
-    a.a_col0 = k * NB; a.b_col0 = k * NB; a.b_tile_rows = NB; a.klen = NB;
+    a.a_col0 = k0 * NB; a.b_col0 = k0 * NB; a.b_tile_rows = NB; a.klen = kw * NB;
     a.c_rows_end = N; a.c_cols_end = N;
     a.epi = EPI_SUB;
     a.batch_a_rows = batch_rows; a.batch_b_rows = batch_rows; a.batch_c_rows = batch_rows;
     if (jhi - jlo == 1) {                       // a single tile column: rows jlo .. nblk-1
       a.tri = 0; a.tiles_m = nblk - jlo; a.tiles_n = 1;
-    } else {                                    // full lower triangle from block jlo on
+    } else {                                    // full lower triangle from block jlo on (jhi == nblk)
       a.tri = 1; a.tiles_m = nblk - jlo; a.tiles_n = nblk - jlo;
     }
     a.a_row0 = jlo * NB; a.b_row0 = jlo * NB;
     a.c_row0 = (long long)jlo * NB; a.c_col0 = (long long)jlo * NB;
-    a.max_tiles_per_cta = lookahead ? 8 : 16;
+    a.max_tiles_per_cta = lookahead ? (kw > 1 ? 4 : 8) : 16;   // keep CTAs short enough for the panel stream
     return launch_gemm(h, mapK, mapK, mapK, a, batch, st);
   };
+  // factor the block columns of one outer panel [b0, b0+w): potf2 + panel solve per 128-column block,
+  // with the in-panel update of the second block column (K = 128)
+  auto outer_panel = [&](int b0, int w, cudaStream_t st) -> int {
+    int r;
+    if ((r = panel(b0, st))) return r;
+    if (w > 1) {
+      if ((r = update(b0, 1, b0 + 1, b0 + 2, st))) return r;
+      if ((r = panel(b0 + 1, st))) return r;
+    }
+    return 0;
+  };
+
+  // Outer panels: width 2 (K = 256 trailing updates: half the C traffic and half the per-tile
+  // prologue/epilogue of K = 128) while the trailing matrix is large enough to hide the longer panel
+  // chain behind the rest-update, width 1 for the tail.  Large batches are throughput-bound in every
+  // launch, so they always use width 2 and no look-ahead.
+  const int wide_min = (batch >= 32) ? 2 : 48;       // remaining block columns needed for a width-2 panel
+  std::vector<int> pb(nblk + 1), pw(nblk + 1);
+  int npanel = 0;
+  for (int b = 0; b < nblk;) {
+    const int w = (nblk - b >= wide_min && b + 1 < nblk) ? 2 : 1;
+    pb[npanel] = b; pw[npanel] = w; npanel++;
+    b += w;
+  }
 
   if (!lookahead) {
-    for (int k = 0; k < nblk; k++) {
-      if ((rc = panel(k, s0))) return rc;
-      if ((rc = update(k, k + 1, nblk, s0))) return rc;
+    for (int P = 0; P < npanel; P++) {
+      if ((rc = outer_panel(pb[P], pw[P], s0))) return rc;
+      if ((rc = update(pb[P], pw[P], pb[P] + pw[P], nblk, s0))) return rc;
     }
     return 0;
   }
 
-  cudaEvent_t* ev_panel = h->ev;            // ev_panel[k]: panel k finished
-  cudaEvent_t* ev_rest = h->ev + nblk + 1;  // ev_rest[k]:  rest-update of step k finished
-  if ((rc = panel(0, s0))) return rc;
+  cudaEvent_t* ev_panel = h->ev;            // ev_panel[P]: outer panel P finished
+  cudaEvent_t* ev_rest = h->ev + nblk + 1;  // ev_rest[P]:  rest-update of outer step P finished
+  if ((rc = outer_panel(pb[0], pw[0], s0))) return rc;
   GPM_CUDA(cudaEventRecord(ev_panel[0], s0));
-  for (int k = 0; k + 1 < nblk; k++) {
-    // helper stream: column k+1 of the step-k update, then panel k+1
-    GPM_CUDA(cudaStreamWaitEvent(s1, ev_panel[k], 0));
-    if (k > 0) GPM_CUDA(cudaStreamWaitEvent(s1, ev_rest[k - 1], 0));
-    if ((rc = update(k, k + 1, k + 2, s1))) return rc;
-    if ((rc = panel(k + 1, s1))) return rc;
-    GPM_CUDA(cudaEventRecord(ev_panel[k + 1], s1));
-    // caller's stream: the rest of the step-k update (tile columns >= k+2)
-    GPM_CUDA(cudaStreamWaitEvent(s0, ev_panel[k], 0));
-    if ((rc = update(k, k + 2, nblk, s0))) return rc;
-    GPM_CUDA(cudaEventRecord(ev_rest[k], s0));
+  for (int P = 0; P + 1 < npanel; P++) {
+    const int b0 = pb[P], w = pw[P], n0 = pb[P + 1], wn = pw[P + 1];
+    // helper stream: the block columns of the next outer panel first, then that panel
+    GPM_CUDA(cudaStreamWaitEvent(s1, ev_panel[P], 0));
+    if (P > 0) GPM_CUDA(cudaStreamWaitEvent(s1, ev_rest[P - 1], 0));
+    for (int c = 0; c < wn; c++)
+      if ((rc = update(b0, w, n0 + c, n0 + c + 1, s1))) return rc;
+    if ((rc = outer_panel(n0, wn, s1))) return rc;
+    GPM_CUDA(cudaEventRecord(ev_panel[P + 1], s1));
+    // caller's stream: the rest of the step-P update (tile columns beyond the next panel)
+    GPM_CUDA(cudaStreamWaitEvent(s0, ev_panel[P], 0));
+    if ((rc = update(b0, w, n0 + wn, nblk, s0))) return rc;
+    GPM_CUDA(cudaEventRecord(ev_rest[P], s0));
   }
-  GPM_CUDA(cudaStreamWaitEvent(s0, ev_panel[nblk - 1], 0));
+  GPM_CUDA(cudaStreamWaitEvent(s0, ev_panel[npanel - 1], 0));
   return 0;
 }
 
