@@ -376,6 +376,15 @@ def run_b200(args):
 
     extra = {"phases_ms": phases, "kernels": kernels, "potrf_info": info}
 
+    # ---- config 1 (the reference-sized case): end-to-end latency, launch-bound, no roofline claim ----
+    X1, Y1, th1 = wl.single_path(200, 1, 2, 2)
+    X1d, Y1d = torch.from_numpy(X1).to(dev), torch.from_numpy(Y1).to(dev)
+
+    def cfg1():
+        m1 = GPmap.fit_gp(X1d, Y1d, theta=th1, check=False)
+        return m1.predict_grid(wl.BOX, (100, 100))
+    extra["cfg1_N200_100x100_latency_ms"] = timed(torch, cfg1, 20, warm=3)
+
     # ---- the other two headline numbers: Cholesky TFLOP/s at N=16384, batched fits/s ---------------
     if not args.no_extra:
         del K, ws

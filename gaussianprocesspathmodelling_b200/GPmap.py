@@ -26,7 +26,7 @@ import numpy as np
 from . import _native
 
 __all__ = ["trajectory", "trajectories", "trajs", "check_if_valid_trajectory", "readcsvfile",
-           "fit_gp", "GPModel", "fit_gp_batched", "lml_sweep", "make_theta"]
+           "fit_gp", "GPModel", "fit_gp_batched", "lml_sweep", "make_theta", "export_raster"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -155,6 +155,18 @@ class GPModel:
         if return_var:
             return out[0].view(Gy, Gx, -1), out[1].view(Gy, Gx)
         return out.view(Gy, Gx, -1)
+
+
+def export_raster(path, mu, var, bounds, shape):
+    """Write posterior rasters over the reference's plot window (GPmap.py:126,155) as an .npz:
+    mu (Gy, Gx, R), var (Gy, Gx), plus the axis vectors.  (matplotlib is not needed)"""
+    import torch
+    x0, x1, y0, y1 = [float(v) for v in bounds]
+    Gx, Gy = int(shape[0]), int(shape[1])
+    to_np = lambda t: t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)  # noqa: E731
+    np.savez_compressed(path, mu=to_np(mu).reshape(Gy, Gx, -1), var=to_np(var).reshape(Gy, Gx),
+                        x=np.linspace(x0, x1, Gx), y=np.linspace(y0, y1, Gy), bounds=np.array([x0, x1, y0, y1]))
+    return path
 
 
 def fit_gp(X, Y, lengthscale=None, signal_var=1.0, noise_var=1e-2, theta=None, check=True, lml=True):
