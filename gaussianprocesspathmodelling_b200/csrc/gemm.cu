@@ -15,7 +15,7 @@ constexpr int STAGES = 3;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int GEMM_THREADS = (CONSUMER_WARPS + 1) * 32;
 constexpr int C_BYTES = NB * NB * 8;
-constexpr int GEMM_SMEM = STAGES * 2 * SLAB_BYTES + C_BYTES + 1024 /*align slack*/ + (2 * STAGES + 2) * 8;
+constexpr int GEMM_SMEM = STAGES * 2 * SLAB_BYTES + C_BYTES + 1024 /*align slack*/ + (2 * STAGES + 3) * 8;
 
 struct TileCoord { int ti, tj; };
 
@@ -34,9 +34,43 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& p, int t) {
   return c;
 }
 
+// One unit of work on a tile: a contraction of nslab slabs and an epilogue.
+struct OpDesc {
+  int nslab, a_col0, b_col0, b_row, epi;
+  long long c_col;
+  bool second_b, rowsq;
+};
+
+__device__ __forceinline__ OpDesc make_op(const GemmArgs& p, const TileCoord& tc, int o, long long bz) {
+  OpDesc d;
+  if (p.sweep_nblk > 0) {
+    const int k = (o + 1) >> 1;
+    const bool isU = (o & 1) != 0;                 // o = 2k-1: update, o = 2k: diagonal multiply
+    d.nslab = isU ? k * (NB / SLAB_K) : NB / SLAB_K;
+    d.a_col0 = isU ? 0 : k * NB;
+    d.b_col0 = 0;
+    d.b_row = k * NB;
+    d.epi = isU ? EPI_SUB : EPI_STORE;
+    d.c_col = (long long)k * NB;
+    d.second_b = !isU;
+    d.rowsq = !isU;
+  } else {
+    d.nslab = p.klen / SLAB_K;
+    d.a_col0 = p.a_col0;
+    d.b_col0 = p.b_col0;
+    d.b_row = p.b_row0 + tc.tj * p.b_tile_rows + (int)(bz * p.batch_b_rows);
+    d.epi = p.epi;
+    d.c_col = p.c_col0 + (long long)tc.tj * NB;
+    d.second_b = false;
+    d.rowsq = p.rowsq != nullptr;
+  }
+  return d;
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const __grid_constant__ CUtensorMap mapC, const GemmArgs p) {
+               const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapB2,
+               const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // swizzle needs 1024 B
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -45,6 +79,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t bar_empty = bar_full + STAGES * 8;
   const uint32_t bar_cfull = bar_empty + STAGES * 8;
   const uint32_t bar_cempty = bar_cfull + 8;
+  const uint32_t bar_dep = bar_cempty + 8;          // sweep mode: previous op's global writes are visible
   double* red = reinterpret_cast<double*>(gen + STAGES * 2 * SLAB_BYTES);  // aliases cbuf (EPI_STORE only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -52,8 +87,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int t_begin = blockIdx.x * p.tiles_per_cta;
   const int t_end = min(total, t_begin + p.tiles_per_cta);
   const long long bz = blockIdx.y;
-  const int nslab = p.klen / SLAB_K;
-  const bool sub = p.epi == EPI_SUB;
+  const int nops = p.sweep_nblk > 0 ? 2 * p.sweep_nblk - 1 : 1;
+  const bool chained = p.sweep_nblk > 0;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -62,6 +97,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     mbar_init(bar_cfull, 1);
     mbar_init(bar_cempty, CONSUMER_WARPS);
+    mbar_init(bar_dep, CONSUMER_WARPS);
     fence_mbar_init();
   }
   __syncthreads();
@@ -71,29 +107,35 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       prefetch_tmap(&mapA);
       prefetch_tmap(&mapB);
-      if (sub) prefetch_tmap(&mapC);
-      const int c_at = min(STAGES - 1, nslab - 1);      // issue the C prefetch after this slab
-      int sg = 0, ct = 0;
+      prefetch_tmap(&mapC);
+      if (chained) prefetch_tmap(&mapB2);
+      int sg = 0, ct = 0, nop = 0;
       for (int t = t_begin; t < t_end; t++) {
         const TileCoord tc = tile_coord(p, t);
         const int a_row = p.a_row0 + tc.ti * NB + (int)(bz * p.batch_a_rows);
-        const int b_row = p.b_row0 + tc.tj * p.b_tile_rows + (int)(bz * p.batch_b_rows);
-        for (int s = 0; s < nslab; s++, sg++) {
-          const int st = sg % STAGES;
-          if (sg >= STAGES) mbar_wait(bar_empty + st * 8, ((sg / STAGES) - 1) & 1);
-          mbar_arrive_expect_tx(bar_full + st * 8, 2 * SLAB_BYTES);
-          const uint32_t dst = base + st * 2 * SLAB_BYTES;
-          tma_load_2d(dst, &mapA, p.a_col0 + s * SLAB_K, a_row, bar_full + st * 8);
-          tma_load_2d(dst + SLAB_BYTES, &mapB, p.b_col0 + s * SLAB_K, b_row, bar_full + st * 8);
-          if (sub && s == c_at) {
-            if (ct > 0) mbar_wait(bar_cempty, (ct - 1) & 1);
-            mbar_arrive_expect_tx(bar_cfull, C_BYTES);
-            const int c_row = (int)(p.c_row0 + (long long)tc.ti * NB + bz * p.batch_c_rows);
-            const int c_col = (int)(p.c_col0 + (long long)tc.tj * NB);
+        for (int o = 0; o < nops; o++, nop++) {
+          const OpDesc d = make_op(p, tc, o, bz);
+          const bool sub = d.epi == EPI_SUB;
+          // chained ops read what the previous op of this CTA stored: wait until it is visible
+          if (chained && nop > 0) mbar_wait(bar_dep, (nop - 1) & 1);
+          const int c_at = min(STAGES - 1, d.nslab - 1);      // issue the C prefetch after this slab
+          for (int s = 0; s < d.nslab; s++, sg++) {
+            const int st = sg % STAGES;
+            if (sg >= STAGES) mbar_wait(bar_empty + st * 8, ((sg / STAGES) - 1) & 1);
+            mbar_arrive_expect_tx(bar_full + st * 8, 2 * SLAB_BYTES);
+            const uint32_t dst = base + st * 2 * SLAB_BYTES;
+            tma_load_2d(dst, &mapA, d.a_col0 + s * SLAB_K, a_row, bar_full + st * 8);
+            tma_load_2d(dst + SLAB_BYTES, d.second_b ? &mapB2 : &mapB, d.b_col0 + s * SLAB_K, d.b_row,
+                        bar_full + st * 8);
+            if (sub && s == c_at) {
+              if (ct > 0) mbar_wait(bar_cempty, (ct - 1) & 1);
+              mbar_arrive_expect_tx(bar_cfull, C_BYTES);
+              const int c_row = (int)(p.c_row0 + (long long)tc.ti * NB + bz * p.batch_c_rows);
 #pragma unroll
-            for (int b = 0; b < NB / SLAB_K; b++)
-              tma_load_2d(cbuf + b * SLAB_BYTES, &mapC, c_col + b * SLAB_K, c_row, bar_cfull);
-            ct++;
+              for (int b = 0; b < NB / SLAB_K; b++)
+                tma_load_2d(cbuf + b * SLAB_BYTES, &mapC, (int)d.c_col + b * SLAB_K, c_row, bar_cfull);
+              ct++;
+            }
           }
         }
       }
@@ -113,108 +155,124 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   for (int t = t_begin; t < t_end; t++) {
     const TileCoord tc = tile_coord(p, t);
-    double acc[8][4][2];
+    for (int o = 0; o < nops; o++) {
+      const OpDesc d = make_op(p, tc, o, bz);
+      const bool sub = d.epi == EPI_SUB;
+      double acc[8][4][2];
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++)
+      for (int mt = 0; mt < 8; mt++)
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-    for (int s = 0; s < nslab; s++, sg++) {
-      const int st = sg % STAGES;
-      mbar_wait(bar_full + st * 8, (sg / STAGES) & 1);
-      const uint32_t sa = base + st * 2 * SLAB_BYTES + a_warp;
-      const uint32_t sb = base + st * 2 * SLAB_BYTES + b_warp;
+      for (int s = 0; s < d.nslab; s++, sg++) {
+        const int st = sg % STAGES;
+        mbar_wait(bar_full + st * 8, (sg / STAGES) & 1);
+        const uint32_t sa = base + st * 2 * SLAB_BYTES + a_warp;
+        const uint32_t sb = base + st * 2 * SLAB_BYTES + b_warp;
 #pragma unroll
-      for (int k4 = 0; k4 < 4; k4++) {
-        double a[8], b[4];
+        for (int k4 = 0; k4 < 4; k4++) {
+          double a[8], b[4];
 #pragma unroll
-        for (int mt = 0; mt < 8; mt++) a[mt] = lds_f64(sa + mt * 1024 + off[k4]);
+          for (int mt = 0; mt < 8; mt++) a[mt] = lds_f64(sa + mt * 1024 + off[k4]);
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) b[nt] = lds_f64(sb + nt * 1024 + off[k4]);
+          for (int nt = 0; nt < 4; nt++) b[nt] = lds_f64(sb + nt * 1024 + off[k4]);
 #pragma unroll
-        for (int mt = 0; mt < 8; mt++)
+          for (int mt = 0; mt < 8; mt++)
 #pragma unroll
-          for (int nt = 0; nt < 4; nt++) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty + st * 8);
-    }
-
-    // ===== epilogue: registers (-> C from smem) -> global, 16-byte stores =====
-    const long long crow_base = p.c_row0 + (long long)tc.ti * NB + wm * 64 + bz * p.batch_c_rows;
-    const long long ccol_base = p.c_col0 + (long long)tc.tj * NB + wn * 32 + 2 * q;
-    if (sub) {
-      mbar_wait(bar_cfull, ct & 1);
-#pragma unroll
-      for (int mt = 0; mt < 8; mt++) {
-        const int r = wm * 64 + mt * 8 + g;
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-          // C tile in smem: 8 boxes of [128 rows x 16 cols], 128B-swizzled; this thread's column pair is
-          // one 16-byte chunk:  box = col/16, chunk = (col%16)/2 ^ (row&7)
-          const uint32_t addr = cbuf + (wn * 2 + (nt >> 1)) * SLAB_BYTES + r * 128 + ((((nt & 1) * 4 + q) ^ g) << 4);
-          double c0, c1;
-          asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c0), "=d"(c1) : "r"(addr));
-          acc[mt][nt][0] = c0 - acc[mt][nt][0];
-          acc[mt][nt][1] = c1 - acc[mt][nt][1];
+            for (int nt = 0; nt < 4; nt++) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + st * 8);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_cempty);
-      ct++;
-    }
+
+      // ===== epilogue: registers (-> C from smem) -> global, 16-byte stores =====
+      const long long crow_base = p.c_row0 + (long long)tc.ti * NB + wm * 64 + bz * p.batch_c_rows;
+      const long long ccol_base = d.c_col + wn * 32 + 2 * q;
+      if (sub) {
+        mbar_wait(bar_cfull, ct & 1);
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++) {
-      const long long row = crow_base + mt * 8 + g;
-      double sq = 0.0;
-      if (row < rows_end) {
-        double* crow = p.C + row * p.ldc;
+        for (int mt = 0; mt < 8; mt++) {
+          const int r = wm * 64 + mt * 8 + g;
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-          const long long col = ccol_base + nt * 8;
-          const double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
-          if (col + 1 < p.c_cols_end) {
-            *reinterpret_cast<double2*>(crow + col) = make_double2(v0, v1);
-            sq += v0 * v0 + v1 * v1;
-          } else if (col < p.c_cols_end) {
-            crow[col] = v0;
-            sq += v0 * v0;
+          for (int nt = 0; nt < 4; nt++) {
+            // C tile in smem: 8 boxes of [128 rows x 16 cols], 128B-swizzled; this thread's column pair is
+            // one 16-byte chunk:  box = col/16, chunk = (col%16)/2 ^ (row&7)
+            const uint32_t addr = cbuf + (wn * 2 + (nt >> 1)) * SLAB_BYTES + r * 128 + ((((nt & 1) * 4 + q) ^ g) << 4);
+            double c0, c1;
+            asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c0), "=d"(c1) : "r"(addr));
+            acc[mt][nt][0] = c0 - acc[mt][nt][0];
+            acc[mt][nt][1] = c1 - acc[mt][nt][1];
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_cempty);
+        ct++;
       }
-      if (p.rowsq) {
-        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-        if (q == 0) red[(wm * 64 + mt * 8 + g) * 4 + wn] = sq;
-      }
-    }
-    if (p.rowsq) {
-      asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
-      if (tid < NB) {
-        const long long row = p.c_row0 + (long long)tc.ti * NB + tid + bz * p.batch_c_rows;
+#pragma unroll
+      for (int mt = 0; mt < 8; mt++) {
+        const long long row = crow_base + mt * 8 + g;
+        double sq = 0.0;
         if (row < rows_end) {
-          const double s4 = (red[tid * 4 + 0] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]);
-          p.rowsq[row + bz * p.batch_rowsq] += s4;
+          double* crow = p.C + row * p.ldc;
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            const long long col = ccol_base + nt * 8;
+            const double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
+            if (col + 1 < p.c_cols_end) {
+              *reinterpret_cast<double2*>(crow + col) = make_double2(v0, v1);
+              sq += v0 * v0 + v1 * v1;
+            } else if (col < p.c_cols_end) {
+              crow[col] = v0;
+              sq += v0 * v0;
+            }
+          }
+        }
+        if (d.rowsq) {
+          sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+          sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+          if (q == 0) red[(wm * 64 + mt * 8 + g) * 4 + wn] = sq;
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
+      if (d.rowsq) {
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
+        if (tid < NB) {
+          const long long row = p.c_row0 + (long long)tc.ti * NB + tid + bz * p.batch_c_rows;
+          if (row < rows_end) {
+            const double s4 = (red[tid * 4 + 0] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]);
+            p.rowsq[row + bz * p.batch_rowsq] += s4;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
+      }
+      if (chained) {
+        // publish this op's global stores to the async proxy (TMA) before the producer loads them
+        fence_proxy_async();
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dep);
+      }
     }
   }
 }
 
 int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& mapB,
-                const CUtensorMap& mapC, const GemmArgs& args_in, int batch, cudaStream_t stream) {
+                const CUtensorMap& mapC, const GemmArgs& args_in, int batch, cudaStream_t stream,
+                const CUtensorMap* mapB2) {
   static bool attr_set = false;
   if (!attr_set) {
     GPM_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     attr_set = true;
   }
   GemmArgs args = args_in;
+  if (args.sweep_nblk > 0) {
+    if (!mapB2 || !args.rowsq || args.tri || args.tiles_n != 1) { set_error("gemm: bad sweep arguments"); return 998; }
+    args.klen = NB;
+  }
   if (args.klen <= 0 || args.klen % SLAB_K != 0) {
     set_error("gemm: contraction length %d is not a positive multiple of %d", args.klen, SLAB_K);
     return 998;
   }
-  if (args.epi == EPI_SUB && args.rowsq) {
+  if (args.sweep_nblk == 0 && args.epi == EPI_SUB && args.rowsq) {
     set_error("gemm: rowsq is only supported with EPI_STORE");
     return 998;
   }
@@ -232,7 +290,7 @@ int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& 
   }
   args.tiles_per_cta = best_c;
   dim3 grid((total + best_c - 1) / best_c, batch);
-  gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(mapA, mapB, mapC, args);
+  gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(mapA, mapB, mapC, mapB2 ? *mapB2 : mapB, args);
   GPM_LAUNCH_CHECK();
   return 0;
 }

@@ -24,6 +24,12 @@ struct GemmArgs {
   // batch (blockIdx.y): rows added per batch index to A, B and C
   long long batch_a_rows, batch_b_rows, batch_c_rows;
   long long batch_rowsq;
+  // Variance-sweep mode (sweep_nblk > 0): a "tile" is a 128-row block of query points and the CTA runs
+  // the whole blocked forward substitution on it, block column by block column:
+  //   D(0), U(1), D(1), U(2), D(2), ...   with  U(k): W[:,k] -= W[:,0:k] L[k,0:k]^T   (B from mapB)
+  //                                             D(k): W[:,k]  = W[:,k] inv(L_kk)^T     (B from mapB2, rowsq)
+  // Each op reads what the previous one wrote (through global memory, generic -> async proxy fence).
+  int sweep_nblk;
   int tiles_per_cta;      // filled by launch_gemm: consecutive tiles one CTA works through
   int max_tiles_per_cta;  // 0 = default (16); the look-ahead Cholesky caps it so that SMs free up regularly
 };
@@ -35,6 +41,7 @@ inline int gemm_grid_x(const GemmArgs& a) {
 
 // mapC describes the matrix args.C points into (used to prefetch C tiles by TMA when epi == EPI_SUB)
 int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& mapB,
-                const CUtensorMap& mapC, const GemmArgs& args, int batch, cudaStream_t stream);
+                const CUtensorMap& mapC, const GemmArgs& args, int batch, cudaStream_t stream,
+                const CUtensorMap* mapB2 = nullptr);
 
 }  // namespace gpm

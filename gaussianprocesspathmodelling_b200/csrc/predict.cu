@@ -7,6 +7,8 @@
 // accumulates the row sums of squares, so var[m] = signal_var - sum_i W[m,i]^2 needs no extra pass.
 // Queries are processed in chunks whose W fits the caller's workspace; chunk sizes are multiples
 // of (SM count x 128) rows so that every GEMM launch is a whole number of waves.
+#include <stdlib.h>
+
 #include "gemm.cuh"
 
 namespace gpm {
@@ -97,19 +99,28 @@ extern "C" int gpm_predict(gpm_handle_t handle, const double* X, int64_t N, int3
     const int tiles = (int)((mc + NB - 1) / NB);
     GPM_CUDA(cudaMemsetAsync(rowsq, 0, (size_t)mc * sizeof(double), st));
     if ((rc = launch_cross_cov_t(X, N, D, th, Xs, grid, m0 + c0, mc, W, npad, npad, st))) return rc;
-    for (int k = 0; k < nblk; k++) {
-      GemmArgs a = {};
-      a.C = W; a.ldc = npad;
-      a.tiles_m = tiles; a.tiles_n = 1; a.tri = 0;
-      a.a_row0 = 0; a.b_row0 = k * NB; a.b_tile_rows = 0;
-      a.c_row0 = 0; a.c_col0 = (long long)k * NB;
-      a.c_rows_end = mc; a.c_cols_end = (long long)(k + 1) * NB;
-      if (k > 0) {                       // W[:,k] -= W[:,0:k] L[k,0:k]^T
-        a.a_col0 = 0; a.b_col0 = 0; a.klen = k * NB; a.epi = EPI_SUB; a.rowsq = nullptr;
-        if ((rc = launch_gemm(h, mapW, mapL, mapW, a, 1, st))) return rc;
+    const bool per_step = getenv("GPM_VAR_STEPS") != nullptr;        // debugging: one launch per block column
+    GemmArgs a = {};
+    a.C = W; a.ldc = npad;
+    a.tiles_m = tiles; a.tiles_n = 1; a.tri = 0;
+    a.a_row0 = 0; a.b_tile_rows = 0;
+    a.c_row0 = 0; a.c_rows_end = mc;
+    if (!per_step) {
+      // the whole blocked forward substitution in one persistent launch
+      a.c_cols_end = npad; a.rowsq = rowsq; a.sweep_nblk = nblk; a.epi = EPI_STORE; a.klen = NB;
+      if ((rc = launch_gemm(h, mapW, mapL, mapW, a, 1, st, &mapInv))) return rc;
+    } else {
+      for (int k = 0; k < nblk; k++) {
+        a.b_row0 = k * NB;
+        a.c_col0 = (long long)k * NB;
+        a.c_cols_end = (long long)(k + 1) * NB;
+        if (k > 0) {                       // W[:,k] -= W[:,0:k] L[k,0:k]^T
+          a.a_col0 = 0; a.b_col0 = 0; a.klen = k * NB; a.epi = EPI_SUB; a.rowsq = nullptr;
+          if ((rc = launch_gemm(h, mapW, mapL, mapW, a, 1, st))) return rc;
+        }
+        a.a_col0 = k * NB; a.b_col0 = 0; a.klen = NB; a.epi = EPI_STORE; a.rowsq = rowsq;   // W[:,k] *= inv(L_kk)^T
+        if ((rc = launch_gemm(h, mapW, mapInv, mapW, a, 1, st))) return rc;
       }
-      a.a_col0 = k * NB; a.b_col0 = 0; a.klen = NB; a.epi = EPI_STORE; a.rowsq = rowsq;   // W[:,k] *= inv(L_kk)^T
-      if ((rc = launch_gemm(h, mapW, mapInv, mapW, a, 1, st))) return rc;
     }
     var_finalize_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, st>>>(rowsq, mc, base, var + c0);
     GPM_LAUNCH_CHECK();
