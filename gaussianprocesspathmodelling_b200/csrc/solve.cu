@@ -172,28 +172,54 @@ lml_kernel(const double* __restrict__ L, long long ldl, long long N, const doubl
 // flag value is the call's epoch so the arrays never need clearing).  L is streamed from HBM once
 // per direction with 128 KB in flight per CTA; the critical path is one flag hand-off per block.
 // ------------------------------------------------------------------------------------------------
+// acc[0..RR) += s * zrow[0..RR)  with 128-bit shared loads (zrow 16-byte aligned when RR is even)
+template <int RR>
+__device__ __forceinline__ void fma_row(double (&acc)[RR], double s, const double* zrow) {
+  if constexpr (RR == 1) {
+    acc[0] = fma(s, zrow[0], acc[0]);
+  } else {
+#pragma unroll
+    for (int r2 = 0; r2 < RR / 2; r2++) {
+      const double2 v = *reinterpret_cast<const double2*>(zrow + 2 * r2);
+      acc[2 * r2] = fma(s, v.x, acc[2 * r2]);
+      acc[2 * r2 + 1] = fma(s, v.y, acc[2 * r2 + 1]);
+    }
+  }
+}
+
 constexpr int CH_THREADS = 512;
 constexpr int ILD = NB + 1;
 constexpr int CHAIN_SMEM = (NB * ILD + NB * RMAX + 4 * NB * RMAX) * 8;
 
 __device__ __forceinline__ void flag_wait(const int* f, int epoch) {
+  // spin with relaxed loads (an acquire load invalidates L1 on every iteration: CCTL.IVALL), then
+  // one acquire fence once the flag is seen
   int v;
   do {
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
   } while (v != epoch);
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void flag_set(int* f, int epoch) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
 }
 
-template <bool BWD>
+#ifdef GPM_SOLVE_TIMING
+__device__ unsigned long long g_solve_ts[10 * 8192];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ST_MARK(slot, blk) if (!BWD && threadIdx.x == 0) g_solve_ts[(slot) * 8192 + (blk)] = gtime();
+#else
+#define ST_MARK(slot, blk)
+#endif
+
+template <bool BWD, int RR>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 solve_chain_kernel(const double* __restrict__ L, long long ldl, long long N, const double* __restrict__ invD,
                    double* z, int R, int nblk, int* flags, int epoch) {
   extern __shared__ double csm[];
   double* sinv = csm;                       // [128][ILD]  inverse of this block's diagonal block
-  double* zs = sinv + NB * ILD;             // [128][RMAX] the dependency block just received
-  double* part = zs + NB * RMAX;            // [4][128][RMAX] partial sums of the four quarters
+  double* zs = sinv + NB * ILD;             // [128][RR] the dependency block just received
+  double* part = zs + NB * RR;              // [4][128][RR] partial sums of the four quarters
   const int tid = threadIdx.x;
   const int e = tid & 127, qd = tid >> 7;   // element (row fwd / column bwd) and quarter of the tile
   const int G = gridDim.x;
@@ -204,9 +230,12 @@ solve_chain_kernel(const double* __restrict__ L, long long ldl, long long N, con
     // stage inv(L_ii) (off the critical path)
     const double* Di = invD + (long long)i * NB * NB;
     for (int idx = tid; idx < NB * NB; idx += CH_THREADS) sinv[(idx >> 7) * ILD + (idx & 127)] = Di[idx];
-    double acc[RMAX];
+    double acc[RR], rhs[RR];
 #pragma unroll
-    for (int r = 0; r < RMAX; r++) acc[r] = 0.0;
+    for (int r = 0; r < RR; r++) {
+      acc[r] = 0.0;
+      rhs[r] = (tid < NB && i0 + tid < N && r < R) ? z[(i0 + tid) * R + r] : 0.0;   // own right-hand side, off the chain
+    }
 
     const int ndep = BWD ? nblk - 1 - i : i;
     for (int dd = 0; dd < ndep; dd++) {
@@ -229,74 +258,79 @@ solve_chain_kernel(const double* __restrict__ L, long long ldl, long long N, con
           seg[r] = (gr < N) ? __ldcs(L + gr * ldl + i0 + e) : 0.0;
         }
       }
+      if (dd == ndep - 1) { ST_MARK(0, i) }       // ready for the last dependency
       if (tid == 0) flag_wait(flags + j, epoch);
+      if (dd == ndep - 1) { ST_MARK(1, i) }       // last dependency seen
       __syncthreads();
       for (int idx = tid; idx < NB * R; idx += CH_THREADS) {
         const long long gr = j0 + idx / R;
-        zs[(idx / R) * RMAX + idx % R] = (gr < N) ? __ldcg(z + j0 * R + idx) : 0.0;
+        zs[(idx / R) * RR + idx % R] = (gr < N) ? __ldcg(z + j0 * R + idx) : 0.0;
       }
       __syncthreads();
+      if (dd == ndep - 1) { ST_MARK(3, i) }       // z_j staged
 #pragma unroll
-      for (int c = 0; c < 32; c++) {
-#pragma unroll
-        for (int r = 0; r < RMAX; r++) if (r < R) acc[r] = fma(seg[c], zs[(32 * qd + c) * RMAX + r], acc[r]);
-      }
+      for (int c = 0; c < 32; c++) fma_row<RR>(acc, seg[c], zs + (32 * qd + c) * RR);
     }
     // combine the quarters: y = rhs - sum
     __syncthreads();
+    ST_MARK(4, i)                                  // tile product done
 #pragma unroll
-    for (int r = 0; r < RMAX; r++) if (r < R) part[(qd * NB + e) * RMAX + r] = acc[r];
+    for (int r = 0; r < RR; r++) part[(qd * NB + e) * RR + r] = acc[r];
     __syncthreads();
     if (tid < NB) {
-      const long long gr = i0 + tid;
 #pragma unroll
-      for (int r = 0; r < RMAX; r++) {
-        if (r < R) {
-          const double s = (part[(0 * NB + tid) * RMAX + r] + part[(1 * NB + tid) * RMAX + r]) +
-                           (part[(2 * NB + tid) * RMAX + r] + part[(3 * NB + tid) * RMAX + r]);
-          zs[tid * RMAX + r] = (gr < N) ? z[gr * R + r] - s : 0.0;
-        }
+      for (int r = 0; r < RR; r++) {
+        const double s = (part[(0 * NB + tid) * RR + r] + part[(1 * NB + tid) * RR + r]) +
+                         (part[(2 * NB + tid) * RR + r] + part[(3 * NB + tid) * RR + r]);
+        zs[tid * RR + r] = rhs[r] - s;
       }
     }
     __syncthreads();
+    ST_MARK(5, i)                                  // y formed
     // multiply by inv(L_ii) (forward) or inv(L_ii)^T (backward) from shared memory
 #pragma unroll
-    for (int r = 0; r < RMAX; r++) acc[r] = 0.0;
+    for (int r = 0; r < RR; r++) acc[r] = 0.0;
 #pragma unroll 8
     for (int c = 0; c < 32; c++) {
       const int k = 32 * qd + c;
       const double d = BWD ? sinv[k * ILD + e] : sinv[e * ILD + k];
-#pragma unroll
-      for (int r = 0; r < RMAX; r++) if (r < R) acc[r] = fma(d, zs[k * RMAX + r], acc[r]);
+      fma_row<RR>(acc, d, zs + k * RR);
     }
 #pragma unroll
-    for (int r = 0; r < RMAX; r++) if (r < R) part[(qd * NB + e) * RMAX + r] = acc[r];
+    for (int r = 0; r < RR; r++) part[(qd * NB + e) * RR + r] = acc[r];
     __syncthreads();
+    ST_MARK(6, i)                                  // inverse-block product done
     if (tid < NB) {
       const long long gr = i0 + tid;
       if (gr < N) {
 #pragma unroll
-        for (int r = 0; r < RMAX; r++) {
+        for (int r = 0; r < RR; r++) {
           if (r < R)
-            z[gr * R + r] = (part[(0 * NB + tid) * RMAX + r] + part[(1 * NB + tid) * RMAX + r]) +
-                            (part[(2 * NB + tid) * RMAX + r] + part[(3 * NB + tid) * RMAX + r]);
+            z[gr * R + r] = (part[(0 * NB + tid) * RR + r] + part[(1 * NB + tid) * RR + r]) +
+                            (part[(2 * NB + tid) * RR + r] + part[(3 * NB + tid) * RR + r]);
         }
       }
-      __threadfence();
     }
-    __syncthreads();
-    if (tid == 0) flag_set(flags + i, epoch);
+    __syncthreads();            // orders the block's stores before thread 0's release (cumulativity)
+    ST_MARK(7, i)                                  // z stored
+    if (tid == 0) { __threadfence(); flag_set(flags + i, epoch); }
+    ST_MARK(2, i)                                 // published
   }
 }
 
+#ifdef GPM_SOLVE_TIMING
+extern "C" void gpm_debug_solve_ts(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_solve_ts, sizeof(g_solve_ts)); }
+#endif
+
 int solve_chain(gpm_handle_impl* h, const double* L, long long N, long long ldl, const double* invD,
                 double* alpha, int R, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    GPM_CUDA(cudaFuncSetAttribute(solve_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
-    GPM_CUDA(cudaFuncSetAttribute(solve_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
-    attr_set = true;
-  }
+  const void* fns[2];
+  if (R <= 1) { fns[0] = (const void*)solve_chain_kernel<false, 1>; fns[1] = (const void*)solve_chain_kernel<true, 1>; }
+  else if (R <= 2) { fns[0] = (const void*)solve_chain_kernel<false, 2>; fns[1] = (const void*)solve_chain_kernel<true, 2>; }
+  else if (R <= 4) { fns[0] = (const void*)solve_chain_kernel<false, 4>; fns[1] = (const void*)solve_chain_kernel<true, 4>; }
+  else { fns[0] = (const void*)solve_chain_kernel<false, 8>; fns[1] = (const void*)solve_chain_kernel<true, 8>; }
+  for (int d = 0; d < 2; d++)
+    GPM_CUDA(cudaFuncSetAttribute(fns[d], cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM));
   int nblk = (int)((N + NB - 1) / NB);
   if (nblk > h->n_flags) { set_error("solve: N too large for the handle's flag arrays"); return 997; }
   int grid = nblk < h->sm_count ? nblk : h->sm_count;
@@ -305,8 +339,7 @@ int solve_chain(gpm_handle_impl* h, const double* L, long long N, long long ldl,
     int* flags = h->flags + dir * h->n_flags;
     void* args[] = {(void*)&L, (void*)&ldl, (void*)&N, (void*)&invD, (void*)&alpha, (void*)&R, (void*)&nblk,
                     (void*)&flags, (void*)&epoch};
-    const void* fn = dir == 0 ? (const void*)solve_chain_kernel<false> : (const void*)solve_chain_kernel<true>;
-    GPM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(CH_THREADS), args, CHAIN_SMEM, stream));
+    GPM_CUDA(cudaLaunchCooperativeKernel(fns[dir], dim3(grid), dim3(CH_THREADS), args, CHAIN_SMEM, stream));
     count_launch(1);
   }
   return 0;
@@ -319,14 +352,15 @@ int solve_chain(gpm_handle_impl* h, const double* L, long long N, long long ldl,
 // ------------------------------------------------------------------------------------------------
 constexpr int SB_MAXN = 2048;
 
+template <int RR>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 solve_path_kernel(const double* __restrict__ Lb, long long ldl, long long N, const double* __restrict__ invDb,
                   const double* __restrict__ Yb, double* __restrict__ alphab, double* __restrict__ lmlb,
                   int R, int nblk, long long batch_l, long long batch_inv, long long batch_y) {
   extern __shared__ double psm[];
-  double* zs = psm;                                   // [nblk*128][RMAX]
-  double* part = zs + (long long)nblk * NB * RMAX;    // [4][128][RMAX]
-  double* ys = part + 4 * NB * RMAX;                  // [128][RMAX]
+  double* zs = psm;                                   // [nblk*128][RR]
+  double* part = zs + (long long)nblk * NB * RR;      // [4][128][RR]
+  double* ys = part + 4 * NB * RR;                    // [128][RR]
   __shared__ double red[CH_THREADS / 32][RMAX + 1];
   const double* L = Lb + blockIdx.x * batch_l;
   const double* invD = invDb + blockIdx.x * batch_inv;
@@ -334,8 +368,8 @@ solve_path_kernel(const double* __restrict__ Lb, long long ldl, long long N, con
   double* alpha = alphab + blockIdx.x * batch_y;
   const int tid = threadIdx.x, e = tid & 127, qd = tid >> 7, warp = tid >> 5, lane = tid & 31;
 
-  for (int idx = tid; idx < nblk * NB * RMAX; idx += CH_THREADS) {
-    const int row = idx / RMAX, r = idx % RMAX;
+  for (int idx = tid; idx < nblk * NB * RR; idx += CH_THREADS) {
+    const int row = idx / RR, r = idx % RR;
     zs[idx] = (row < N && r < R) ? Y[(long long)row * R + r] : 0.0;
   }
   double logdet = 0.0;
@@ -346,9 +380,9 @@ solve_path_kernel(const double* __restrict__ Lb, long long ldl, long long N, con
     for (int it = 0; it < nblk; it++) {
       const int i = dir ? nblk - 1 - it : it;
       const long long i0 = (long long)i * NB;
-      double acc[RMAX];
+      double acc[RR];
 #pragma unroll
-      for (int r = 0; r < RMAX; r++) acc[r] = 0.0;
+      for (int r = 0; r < RR; r++) acc[r] = 0.0;
       const int ndep = dir ? nblk - 1 - i : i;
       for (int dd = 0; dd < ndep; dd++) {
         const int j = dir ? nblk - 1 - dd : dd;
@@ -369,12 +403,9 @@ solve_path_kernel(const double* __restrict__ Lb, long long ldl, long long N, con
             seg[r] = (gr < N) ? __ldcs(L + gr * ldl + i0 + e) : 0.0;
           }
         }
-        const double* zj = zs + (j0 + 32 * qd) * RMAX;
+        const double* zj = zs + (j0 + 32 * qd) * RR;
 #pragma unroll
-        for (int c = 0; c < 32; c++) {
-#pragma unroll
-          for (int r = 0; r < RMAX; r++) if (r < R) acc[r] = fma(seg[c], zj[c * RMAX + r], acc[r]);
-        }
+        for (int c = 0; c < 32; c++) fma_row<RR>(acc, seg[c], zj + c * RR);
       }
       // diagonal-block inverse segment (issued before the reduction barriers)
       double dseg[32];
@@ -390,37 +421,30 @@ solve_path_kernel(const double* __restrict__ Lb, long long ldl, long long N, con
         }
       }
 #pragma unroll
-      for (int r = 0; r < RMAX; r++) if (r < R) part[(qd * NB + e) * RMAX + r] = acc[r];
+      for (int r = 0; r < RR; r++) part[(qd * NB + e) * RR + r] = acc[r];
       __syncthreads();
       if (tid < NB) {
 #pragma unroll
-        for (int r = 0; r < RMAX; r++) {
-          if (r < R) {
-            const double sgm = (part[(0 * NB + tid) * RMAX + r] + part[(1 * NB + tid) * RMAX + r]) +
-                               (part[(2 * NB + tid) * RMAX + r] + part[(3 * NB + tid) * RMAX + r]);
-            ys[tid * RMAX + r] = zs[(i0 + tid) * RMAX + r] - sgm;
-          }
+        for (int r = 0; r < RR; r++) {
+          const double sgm = (part[(0 * NB + tid) * RR + r] + part[(1 * NB + tid) * RR + r]) +
+                             (part[(2 * NB + tid) * RR + r] + part[(3 * NB + tid) * RR + r]);
+          ys[tid * RR + r] = zs[(i0 + tid) * RR + r] - sgm;
         }
       }
       __syncthreads();
 #pragma unroll
-      for (int r = 0; r < RMAX; r++) acc[r] = 0.0;
+      for (int r = 0; r < RR; r++) acc[r] = 0.0;
 #pragma unroll
-      for (int c = 0; c < 32; c++) {
+      for (int c = 0; c < 32; c++) fma_row<RR>(acc, dseg[c], ys + (32 * qd + c) * RR);
 #pragma unroll
-        for (int r = 0; r < RMAX; r++) if (r < R) acc[r] = fma(dseg[c], ys[(32 * qd + c) * RMAX + r], acc[r]);
-      }
-#pragma unroll
-      for (int r = 0; r < RMAX; r++) if (r < R) part[(qd * NB + e) * RMAX + r] = acc[r];
+      for (int r = 0; r < RR; r++) part[(qd * NB + e) * RR + r] = acc[r];
       __syncthreads();
       if (tid < NB) {
 #pragma unroll
-        for (int r = 0; r < RMAX; r++) {
-          if (r < R) {
-            const double v = (part[(0 * NB + tid) * RMAX + r] + part[(1 * NB + tid) * RMAX + r]) +
-                             (part[(2 * NB + tid) * RMAX + r] + part[(3 * NB + tid) * RMAX + r]);
-            zs[(i0 + tid) * RMAX + r] = (i0 + tid < N) ? v : 0.0;
-          }
+        for (int r = 0; r < RR; r++) {
+          const double v = (part[(0 * NB + tid) * RR + r] + part[(1 * NB + tid) * RR + r]) +
+                           (part[(2 * NB + tid) * RR + r] + part[(3 * NB + tid) * RR + r]);
+          zs[(i0 + tid) * RR + r] = (i0 + tid < N) ? v : 0.0;
         }
       }
       __syncthreads();
@@ -433,9 +457,9 @@ solve_path_kernel(const double* __restrict__ Lb, long long ldl, long long N, con
   acc[RMAX] = logdet;
   for (long long i = tid; i < N; i += CH_THREADS) {
 #pragma unroll
-    for (int r = 0; r < RMAX; r++) {
+    for (int r = 0; r < RR; r++) {
       if (r < R) {
-        const double a = zs[i * RMAX + r];
+        const double a = zs[i * RR + r];
         alpha[i * R + r] = a;
         acc[r] = fma(Y[i * R + r], a, acc[r]);
       }
@@ -462,14 +486,11 @@ int solve_paths(const double* L, long long N, long long ldl, const double* invD,
                 long long batch_y, cudaStream_t stream) {
   const int nblk = (int)((N + NB - 1) / NB);
   if ((long long)nblk * NB > SB_MAXN) return -1;
-  const int smem = (nblk * NB * RMAX + 4 * NB * RMAX + NB * RMAX) * 8;
-  static int attr = 0;
-  if (smem > attr) {
-    GPM_CUDA(cudaFuncSetAttribute(solve_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = smem;
-  }
-  solve_path_kernel<<<batch, CH_THREADS, smem, stream>>>(L, ldl, N, invD, Y, alpha, lml, R, nblk, batch_l,
-                                                         batch_inv, batch_y);
+  const int RR = R <= 1 ? 1 : (R <= 2 ? 2 : (R <= 4 ? 4 : 8));
+  const int smem = (nblk * NB * RR + 4 * NB * RR + NB * RR) * 8;
+  auto kern = RR == 1 ? solve_path_kernel<1> : (RR == 2 ? solve_path_kernel<2> : (RR == 4 ? solve_path_kernel<4> : solve_path_kernel<8>));
+  GPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<batch, CH_THREADS, smem, stream>>>(L, ldl, N, invD, Y, alpha, lml, R, nblk, batch_l, batch_inv, batch_y);
   GPM_LAUNCH_CHECK();
   return 0;
 }

@@ -264,3 +264,99 @@ def test_c_abi_argument_errors():
     assert b"argument 7" in lib.gpm_last_error()
     bad = _native.theta_array([1.0, -1.0, 1.0, 0.1])
     assert lib.gpm_cov(h, C.c_void_p(x.data_ptr()), 8, 2, bad, C.c_void_p(k.data_ptr()), 8, 0, st) == -5
+
+
+def test_cross_cov_materialised_matches_oracle():
+    lib = _native.load(); h = _native.handle(0)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for N, D, M in ((300, 2, 77), (130, 3, 513)):
+        X, _, th = wl.single_path(N, seed=40 + N, D=D)
+        rng = np.random.default_rng(N)
+        Xs = np.column_stack([rng.uniform(-5e4, 5e4, M), rng.uniform(-5e4, 5e4, M)] + ([rng.uniform(0, 60, M)] if D == 3 else []))
+        Xd, Xsd = dev(X), dev(Xs)
+        ld = N + 3
+        out = torch.full((M, ld), float("nan"), dtype=torch.float64, device="cuda")
+        rc = lib.gpm_cross_cov(h, C.c_void_p(Xd.data_ptr()), N, D, _native.theta_array(th), C.c_void_p(Xsd.data_ptr()), None,
+                               0, M, C.c_void_p(out.data_ptr()), ld, st)
+        _native.check(rc, "gpm_cross_cov")
+        want = gp_ref.cross_cov(X, Xs, th).T
+        got = out.cpu().numpy()
+        assert np.abs(got[:, :N] - want).max() < 4e-15
+        assert np.isnan(got[:, N:]).all()                      # nothing written beyond column N
+    # grid form: points [m0, m1) of a regular grid
+    X, _, th = wl.single_path(200, seed=1, D=2)
+    grid = _native.GpmGrid(wl.BOX[0], wl.BOX[1], wl.BOX[2], wl.BOX[3], 0.0, 31, 17)
+    out = torch.empty((100, 200), dtype=torch.float64, device="cuda")
+    Xd = dev(X)
+    rc = lib.gpm_cross_cov(h, C.c_void_p(Xd.data_ptr()), 200, 2, _native.theta_array(th), None, C.byref(grid), 50, 150,
+                           C.c_void_p(out.data_ptr()), 200, st)
+    _native.check(rc, "gpm_cross_cov")
+    P = gp_ref.grid_points(wl.BOX, (31, 17))[50:150]
+    assert np.abs(out.cpu().numpy() - gp_ref.cross_cov(X, P, th).T).max() < 4e-15
+
+
+def test_variance_chunked_workspace_and_per_step_path_agree():
+    # a workspace far smaller than the query set forces the chunk loop; the per-step launch path
+    # (GPM_VAR_STEPS) must give bitwise the same numbers as the fused persistent sweep
+    lib = _native.load(); h = _native.handle(0)
+    X, Y, th = wl.single_path(700, seed=77, D=2, R=2)
+    m = GPmap.fit_gp(X, Y, theta=th)
+    M = 5000
+    rng = np.random.default_rng(5)
+    Xs = dev(np.column_stack([rng.uniform(-5e4, 5e4, M), rng.uniform(-5e4, 5e4, M)]))
+    mu_full, var_full = m.predict(Xs)
+
+    def run(ws_rows):
+        npad = 768
+        ws = torch.empty(ws_rows * (npad + 1), dtype=torch.float64, device="cuda")
+        mu = torch.empty((M, 2), dtype=torch.float64, device="cuda"); var = torch.empty(M, dtype=torch.float64, device="cuda")
+        rc = lib.gpm_predict(h, C.c_void_p(m.X.data_ptr()), 700, 2, _native.theta_array(th), C.c_void_p(m.K.data_ptr()),
+                             m.K.stride(0), C.c_void_p(m.ws.data_ptr()), C.c_void_p(m.alpha.data_ptr()), 2,
+                             C.c_void_p(Xs.data_ptr()), None, 0, M, C.c_void_p(mu.data_ptr()), C.c_void_p(var.data_ptr()),
+                             C.c_void_p(ws.data_ptr()), ws.numel() * 8, 3, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _native.check(rc, "gpm_predict")
+        torch.cuda.synchronize()
+        return mu, var
+
+    mu_c, var_c = run(384)                      # 14 chunks of 384 rows
+    assert torch.equal(mu_c, mu_full) and torch.equal(var_c, var_full)
+    os.environ["GPM_VAR_STEPS"] = "1"
+    try:
+        mu_s, var_s = run(1024)
+    finally:
+        del os.environ["GPM_VAR_STEPS"]
+    assert torch.equal(var_s, var_full)
+    mo = gp_ref.fit(X, Y, th)
+    _, var_o = gp_ref.predict(mo, Xs.cpu().numpy())
+    assert nrm(var_full.cpu().numpy(), var_o) < VAR_TOL
+    # too small a workspace is an argument error, not a crash
+    tiny = torch.empty(16, dtype=torch.float64, device="cuda")
+    rc = lib.gpm_predict(h, C.c_void_p(m.X.data_ptr()), 700, 2, _native.theta_array(th), C.c_void_p(m.K.data_ptr()),
+                         m.K.stride(0), C.c_void_p(m.ws.data_ptr()), C.c_void_p(m.alpha.data_ptr()), 2,
+                         C.c_void_p(Xs.data_ptr()), None, 0, M, C.c_void_p(mu_c.data_ptr()), C.c_void_p(var_c.data_ptr()),
+                         C.c_void_p(tiny.data_ptr()), tiny.numel() * 8, 3, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == -18
+
+
+def test_batched_ragged_and_many_targets():
+    rng = np.random.default_rng(9)
+    for B, N, D, R in ((7, 33, 2, 1), (3, 257, 3, 8), (2, 640, 2, 3)):
+        Xb = np.stack([wl.single_path(N, seed=500 + b, D=D)[0] for b in range(B)])
+        Yb = rng.standard_normal((B, N, R))
+        th = wl.default_theta(D)
+        alpha, lml = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+        a_o, l_o = gp_ref.fit_batched(Xb, Yb, th)
+        assert nrm(alpha.cpu().numpy(), a_o) < MEAN_TOL
+        assert np.abs(lml.cpu().numpy() - l_o).max() < LML_TOL * np.abs(l_o).max()
+    with pytest.raises(np.linalg.LinAlgError):
+        GPmap.fit_gp_batched(np.zeros((2, 40, 2)), np.ones((2, 40, 1)), lengthscale=1.0, noise_var=0.0)
+
+
+def test_export_raster_roundtrip(tmp_path):
+    X, Y, th = wl.single_path(64, seed=3, D=2, R=2)
+    m = GPmap.fit_gp(X, Y, theta=th)
+    mu, var = m.predict_grid(wl.BOX, (12, 9))
+    f = GPmap.export_raster(str(tmp_path / "r.npz"), mu, var, wl.BOX, (12, 9))
+    z = np.load(f)
+    assert z["mu"].shape == (9, 12, 2) and z["var"].shape == (9, 12) and z["x"].shape == (12,)
+    assert np.array_equal(z["var"], var.cpu().numpy())
