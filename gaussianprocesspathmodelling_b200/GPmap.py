@@ -26,7 +26,7 @@ import numpy as np
 from . import _native
 
 __all__ = ["trajectory", "trajectories", "trajs", "check_if_valid_trajectory", "readcsvfile",
-           "fit_gp", "GPModel", "fit_gp_batched", "lml_sweep", "make_theta", "export_raster"]
+           "fit_gp", "GPModel", "fit_gp_batched", "lml_sweep", "make_theta", "export_raster", "optimize_gp"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -104,6 +104,22 @@ class GPModel:
         if j != 0:
             raise np.linalg.LinAlgError(f"covariance matrix is not positive definite: pivot {j} <= 0")
         return self
+
+    def lml_grad(self):
+        """d lml_r / d log(theta_j) as a numpy (R, D+2) array, j over [l_1..l_D, signal_var, noise_var]
+        (R&W eq. 5.9; K^{-1} is formed on the tensor cores)."""
+        torch = _torch()
+        lib = _native.load()
+        h = _native.handle(self.X.device.index or 0)
+        R = self.alpha.shape[1]
+        nbytes = int(lib.gpm_lml_grad_workspace_bytes(self.N))
+        ws = torch.empty(nbytes // 8, dtype=torch.float64, device=self.X.device)
+        grad = torch.empty((R, self.D + 2), dtype=torch.float64, device=self.X.device)
+        rc = lib.gpm_lml_grad(h, _ptr(self.X), self.N, self.D, _native.theta_array(self.theta), _ptr(self.K),
+                              self.K.stride(0), _ptr(self.ws), _ptr(self.alpha), R, _ptr(grad), _ptr(ws), nbytes,
+                              _stream(self.X))
+        _native.check(rc, "gpm_lml_grad")
+        return grad.cpu().numpy()
 
     # -- prediction ---------------------------------------------------------------------------
     def _predict(self, Xs, grid, m0, m1, return_var, include_noise):
@@ -258,6 +274,39 @@ def lml_sweep(X, Y, thetas, indices=None):
     if not out:
         return np.empty((0, 1 if Y.ndim == 1 else Y.shape[1]))
     return torch.stack(out).cpu().numpy()
+
+
+def optimize_gp(X, Y, theta0, maxiter=50, bounds=None, tie_xy=True):
+    """Hyper-parameter learning: maximise sum_r lml_r over log(theta) with L-BFGS-B (scipy on the host,
+    fit + exact gradient on the GPU).  ``tie_xy`` keeps one lengthscale for x and y (isotropic in space),
+    as the sweep of BASELINE config 5 does.  Returns (theta, model, scipy result)."""
+    from scipy.optimize import minimize
+    X = _dev(X)
+    Y = _dev(Y, X.device)
+    D = X.shape[1]
+    theta0 = np.asarray(theta0, dtype=np.float64)
+
+    def unpack(u):
+        th = np.exp(u)
+        if tie_xy:
+            th = np.concatenate([[th[0]], th])          # u = [l_xy, (l_t), sf2, sn2]
+        return th
+
+    def fun(u):
+        th = unpack(u)
+        try:
+            m = fit_gp(X, Y, theta=th, check=True)
+        except np.linalg.LinAlgError:
+            return 1e300, np.zeros_like(u)
+        g = m.lml_grad().sum(axis=0)
+        if tie_xy:
+            g = np.concatenate([[g[0] + g[1]], g[2:]])
+        return -float(m.lml.sum()), -g
+
+    u0 = np.log(theta0[1:] if tie_xy else theta0)
+    res = minimize(fun, u0, jac=True, method="L-BFGS-B", bounds=bounds, options={"maxiter": maxiter})
+    theta = unpack(res.x)
+    return theta, fit_gp(X, Y, theta=theta), res
 
 
 # ------------------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@ the GP entry points does.
 """
 from . import workloads  # noqa: F401
 from . import GPmap  # noqa: F401
-from .GPmap import (GPModel, check_if_valid_trajectory, fit_gp, fit_gp_batched, lml_sweep, make_theta,  # noqa: F401
-                    readcsvfile, trajectories, trajectory)
+from .GPmap import (GPModel, check_if_valid_trajectory, export_raster, fit_gp, fit_gp_batched, lml_sweep,  # noqa: F401
+                    make_theta, optimize_gp, readcsvfile, trajectories, trajectory)
 
 __version__ = "0.1.0"

@@ -42,6 +42,8 @@ SIGNATURES = {
     "gpm_fit_batched_workspace_bytes": (_sz, [_i64, _i64]),
     "gpm_fit_batched": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, C.POINTER(C.c_double), _i64,
                                   _vp, _vp, _vp, _vp, _vp]),
+    "gpm_lml_grad_workspace_bytes": (_sz, [_i64]),
+    "gpm_lml_grad": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double), _vp, _i64, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "gpm_kmeans_assign": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
 }
 

@@ -44,20 +44,22 @@ struct OpDesc {
 __device__ __forceinline__ OpDesc make_op(const GemmArgs& p, const TileCoord& tc, int o, long long bz) {
   OpDesc d;
   if (p.sweep_nblk > 0) {
-    const int k = (o + 1) >> 1;
-    const bool isU = (o & 1) != 0;                 // o = 2k-1: update, o = 2k: diagonal multiply
-    d.nslab = isU ? k * (NB / SLAB_K) : NB / SLAB_K;
-    d.a_col0 = isU ? 0 : k * NB;
-    d.b_col0 = 0;
+    const int k0 = p.sweep_tri ? tc.ti : 0;        // first block column this row block touches
+    const int k = k0 + ((o + 1) >> 1);
+    const bool isU = (o & 1) != 0;                 // o odd: update, o even: diagonal multiply
+    d.nslab = isU ? (k - k0) * (NB / SLAB_K) : NB / SLAB_K;
+    d.a_col0 = isU ? k0 * NB : k * NB;
+    d.b_col0 = isU ? k0 * NB : 0;
     d.b_row = k * NB;
     d.epi = isU ? EPI_SUB : EPI_STORE;
     d.c_col = (long long)k * NB;
     d.second_b = !isU;
     d.rowsq = !isU;
   } else {
-    d.nslab = p.klen / SLAB_K;
-    d.a_col0 = p.a_col0;
-    d.b_col0 = p.b_col0;
+    const int skip = (p.tri && p.tri_kstart) ? tc.ti * NB : 0;
+    d.nslab = (p.klen - skip) / SLAB_K;
+    d.a_col0 = p.a_col0 + skip;
+    d.b_col0 = p.b_col0 + skip;
     d.b_row = p.b_row0 + tc.tj * p.b_tile_rows + (int)(bz * p.batch_b_rows);
     d.epi = p.epi;
     d.c_col = p.c_col0 + (long long)tc.tj * NB;
@@ -87,8 +89,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int t_begin = blockIdx.x * p.tiles_per_cta;
   const int t_end = min(total, t_begin + p.tiles_per_cta);
   const long long bz = blockIdx.y;
-  const int nops = p.sweep_nblk > 0 ? 2 * p.sweep_nblk - 1 : 1;
   const bool chained = p.sweep_nblk > 0;
+  auto ops_of = [&](const TileCoord& tc) {
+    return chained ? 2 * (p.sweep_nblk - (p.sweep_tri ? tc.ti : 0)) - 1 : 1;
+  };
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -113,6 +117,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int t = t_begin; t < t_end; t++) {
         const TileCoord tc = tile_coord(p, t);
         const int a_row = p.a_row0 + tc.ti * NB + (int)(bz * p.batch_a_rows);
+        const int nops = ops_of(tc);
         for (int o = 0; o < nops; o++, nop++) {
           const OpDesc d = make_op(p, tc, o, bz);
           const bool sub = d.epi == EPI_SUB;
@@ -155,6 +160,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   for (int t = t_begin; t < t_end; t++) {
     const TileCoord tc = tile_coord(p, t);
+    const int nops = ops_of(tc);
     for (int o = 0; o < nops; o++) {
       const OpDesc d = make_op(p, tc, o, bz);
       const bool sub = d.epi == EPI_SUB;
@@ -288,6 +294,7 @@ int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& 
     const long long span = ((ctas + slots - 1) / slots) * c;
     if (best_span < 0 || span <= best_span) { best_span = span; best_c = c; }
   }
+  if (args.sweep_tri || args.tri_kstart) best_c = 1;   // tiles differ in work: let the hardware balance them
   args.tiles_per_cta = best_c;
   dim3 grid((total + best_c - 1) / best_c, batch);
   gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(mapA, mapB, mapC, mapB2 ? *mapB2 : mapB, args);

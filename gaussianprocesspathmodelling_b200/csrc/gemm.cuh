@@ -30,6 +30,9 @@ struct GemmArgs {
   //                                             D(k): W[:,k]  = W[:,k] inv(L_kk)^T     (B from mapB2, rowsq)
   // Each op reads what the previous one wrote (through global memory, generic -> async proxy fence).
   int sweep_nblk;
+  int sweep_tri;          // sweep mode on a block-upper-triangular right-hand side (row block t is zero left of
+                          // block column t): row block t starts at op D(t) and contracts from column t*NB
+  int tri_kstart;         // tile mode, tri != 0: operands are zero left of block column ti -> contract from ti*NB
   int tiles_per_cta;      // filled by launch_gemm: consecutive tiles one CTA works through
   int max_tiles_per_cta;  // 0 = default (16); the look-ahead Cholesky caps it so that SMs free up regularly
 };

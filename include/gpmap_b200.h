@@ -117,6 +117,15 @@ int gpm_fit_batched(gpm_handle_t h, const double* Xb, const double* Yb, int64_t 
                     int32_t D, int32_t R, const double* theta, int64_t theta_stride,
                     double* alpha, double* lml, int32_t* info, void* ws, gpm_stream_t stream);
 
+/* exact gradient of the log marginal likelihood with respect to the LOG
+ * hyper-parameters,  grad[r, j] = d lml_r / d log(theta_j),  j over [l_1..l_D, signal_var, noise_var]
+ * (R&W eq. 5.9).  Needs the factor and alpha of a finished fit.  K^{-1} is formed on the tensor cores
+ * (2 N^3 / 3 flops).  grad: device R x (D+2).  ws: gpm_lml_grad_workspace_bytes(N) bytes. */
+size_t gpm_lml_grad_workspace_bytes(int64_t N);
+int gpm_lml_grad(gpm_handle_t h, const double* X, int64_t N, int32_t D, const double* theta,
+                 const double* L, int64_t ldl, const void* potrf_ws, const double* alpha, int32_t R,
+                 double* grad, void* ws, size_t ws_bytes, gpm_stream_t stream);
+
 /* "Next" row of SURVEY.md section 8f: the reference's actual hot loop, trajectories.calc_distance
  * inside kmeansclustering (GPmap.py:72-80,114-121): dist[p, c] = sum_i ||path_p[i] - centroid_c[i]||_2,
  * assign[p] = first c with the smallest distance (strict '<' as GPmap.py:76).

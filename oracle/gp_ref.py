@@ -159,6 +159,37 @@ def lml_sweep(X, Y, thetas):
     return np.stack([fit(X, Y, th)["lml"] for th in thetas])
 
 
+def lml_grad(X, Y, theta):
+    """Gradient of the log marginal likelihood w.r.t. the LOG hyper-parameters (R&W eq. 5.9):
+
+        d lml_r / d log(theta_j) = 0.5 * alpha_r^T dK_j alpha_r - 0.5 * tr(K^{-1} dK_j),
+        dK_j = dK / d log(theta_j):   l_d -> K_f * ((x_d - z_d) / l_d)^2,   signal_var -> K_f,
+                                      noise_var -> noise_var * I.
+    Returns (R, D + 2)."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.ndim == 1:
+        Y = Y[:, None]
+    N, D = X.shape
+    ls, sf2, sn2 = split_theta(theta, D)
+    m = fit(X, Y, theta)
+    Linv = solve_triangular(m["L"], np.eye(N), lower=True)
+    Kinv = Linv.T @ Linv
+    Kf = cross_cov(X, X, theta)
+    dKs = []
+    for d in range(D):
+        diff = (X[:, d][:, None] - X[:, d][None, :]) / ls[d]
+        dKs.append(Kf * diff * diff)
+    dKs.append(Kf)
+    dKs.append(sn2 * np.eye(N))
+    a = m["alpha"]
+    g = np.empty((Y.shape[1], D + 2))
+    for j, dK in enumerate(dKs):
+        tr = np.sum(Kinv * dK)
+        g[:, j] = 0.5 * np.einsum("nr,nm,mr->r", a, dK, a) - 0.5 * tr
+    return g
+
+
 # ----------------------------------------------------------------------------------------------
 # Restatement of the code the reference DOES contain (SURVEY.md section 8f "next" rows): the
 # trajectory distance, centroid mean and ingest filter.  These are pinned against the reference

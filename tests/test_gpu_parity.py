@@ -360,3 +360,36 @@ def test_export_raster_roundtrip(tmp_path):
     z = np.load(f)
     assert z["mu"].shape == (9, 12, 2) and z["var"].shape == (9, 12) and z["x"].shape == (12,)
     assert np.array_equal(z["var"], var.cpu().numpy())
+
+
+@pytest.mark.parametrize("N,D,R", [(33, 2, 1), (130, 3, 2), (300, 2, 8), (700, 3, 2)])
+def test_lml_gradient_vs_oracle(N, D, R):
+    X, Y2, th = wl.single_path(N, seed=60 + N, D=D, R=2)
+    Y = np.random.default_rng(N).standard_normal((N, R))
+    m = GPmap.fit_gp(X, Y, theta=th)
+    g = m.lml_grad()
+    go = gp_ref.lml_grad(X, Y, th)
+    assert g.shape == (R, D + 2)
+    assert np.abs(g - go).max() < 1e-7 * np.abs(go).max()
+
+
+def test_lml_gradient_config2_size_finite_difference():
+    # N=4096: compare the analytic gradient with central differences of the GPU LML itself
+    X, Y, th = wl.single_path(4096, seed=2, D=2, R=2)
+    g = GPmap.fit_gp(X, Y, theta=th).lml_grad()
+    for j in (0, 2, 3):
+        h = 1e-4
+        tp, tm = th.copy(), th.copy()
+        tp[j] *= np.exp(h); tm[j] *= np.exp(-h)
+        fd = (GPmap.fit_gp(X, Y, theta=tp).lml - GPmap.fit_gp(X, Y, theta=tm).lml) / (2 * h)
+        assert np.allclose(g[:, j], fd, rtol=1e-4, atol=1e-5 * np.abs(g).max())
+
+
+def test_optimize_gp_improves_the_likelihood():
+    X, Y, th = wl.single_path(400, seed=14, D=2, R=1)
+    th0 = np.array([3000.0, 3000.0, 0.5, 0.5])
+    m0 = GPmap.fit_gp(X, Y, theta=th0)
+    theta, m, res = GPmap.optimize_gp(X, Y, th0, maxiter=25)
+    assert m.lml.sum() > m0.lml.sum() + 1.0
+    assert theta[0] == theta[1] and np.all(theta > 0)
+    assert np.abs(m.lml_grad().sum(0)[2:]).max() < 1e-2 * max(1.0, abs(m.lml.sum()))

@@ -148,3 +148,15 @@ def test_reference_restatements_match_the_reference(ref_golden):
             # np.linalg.norm uses BLAS ddot (FMA on this CPU), so agreement is to an ulp or two.
             d = gp_ref.calc_distance(g["cx"][c], g["cy"][c], xs[p], ys[p])
             assert abs(d - g["d2c"][p, c]) <= 1e-15 * g["d2c"][p, c]
+
+
+def test_lml_grad_matches_finite_differences():
+    X, Y, th = wl.single_path(60, seed=8, D=3, R=2)
+    g = gp_ref.lml_grad(X, Y, th)
+    assert g.shape == (2, 5)
+    for j in range(5):
+        h = 1e-5
+        tp, tm = th.copy(), th.copy()
+        tp[j] *= np.exp(h); tm[j] *= np.exp(-h)
+        fd = (gp_ref.fit(X, Y, tp)["lml"] - gp_ref.fit(X, Y, tm)["lml"]) / (2 * h)
+        assert np.allclose(g[:, j], fd, rtol=2e-6, atol=1e-6 * np.abs(g).max())
