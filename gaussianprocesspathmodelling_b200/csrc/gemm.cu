@@ -86,8 +86,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int total = p.tri ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
-  const int t_begin = blockIdx.x * p.tiles_per_cta;
-  const int t_end = min(total, t_begin + p.tiles_per_cta);
+  // tiles of this CTA: a run of consecutive tiles, or (triangular sweep) the pair (b, tiles_m-1-b), which
+  // balances the quadratically decreasing work of the row blocks
+  const int t_begin = p.sweep_tri ? 0 : blockIdx.x * p.tiles_per_cta;
+  const int t_end = p.sweep_tri ? ((2 * (int)blockIdx.x == p.tiles_m - 1) ? 1 : 2) : min(total, t_begin + p.tiles_per_cta);
+  auto tile_id = [&](int t) { return p.sweep_tri ? (t == 0 ? (int)blockIdx.x : p.tiles_m - 1 - (int)blockIdx.x) : t; };
   const long long bz = blockIdx.y;
   const bool chained = p.sweep_nblk > 0;
   auto ops_of = [&](const TileCoord& tc) {
@@ -115,7 +118,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (chained) prefetch_tmap(&mapB2);
       int sg = 0, ct = 0, nop = 0;
       for (int t = t_begin; t < t_end; t++) {
-        const TileCoord tc = tile_coord(p, t);
+        const TileCoord tc = tile_coord(p, tile_id(t));
         const int a_row = p.a_row0 + tc.ti * NB + (int)(bz * p.batch_a_rows);
         const int nops = ops_of(tc);
         for (int o = 0; o < nops; o++, nop++) {
@@ -159,7 +162,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   int sg = 0, ct = 0;
 
   for (int t = t_begin; t < t_end; t++) {
-    const TileCoord tc = tile_coord(p, t);
+    const TileCoord tc = tile_coord(p, tile_id(t));
     const int nops = ops_of(tc);
     for (int o = 0; o < nops; o++) {
       const OpDesc d = make_op(p, tc, o, bz);
@@ -296,7 +299,7 @@ int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& 
   }
   if (args.sweep_tri || args.tri_kstart) best_c = 1;   // tiles differ in work: let the hardware balance them
   args.tiles_per_cta = best_c;
-  dim3 grid((total + best_c - 1) / best_c, batch);
+  dim3 grid(args.sweep_tri ? (total + 1) / 2 : (total + best_c - 1) / best_c, batch);
   gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(mapA, mapB, mapC, mapB2 ? *mapB2 : mapB, args);
   GPM_LAUNCH_CHECK();
   return 0;
