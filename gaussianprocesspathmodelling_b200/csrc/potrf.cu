@@ -17,11 +17,19 @@
 
 namespace gpm {
 
-constexpr int PLD = NB + 4;   // smem pitch (doubles) of the 128x128 block: = 4 mod 16 makes DMMA A/B fragment reads
-                              // conflict-free and keeps rows 16-byte aligned for 128-bit C-fragment accesses
-constexpr int XLD = 12;
-constexpr int P2_THREADS = 512, P2_WARPS = P2_THREADS / 32;   // potf2 CTA: latency-bound, so more warps help       // pitch of the 8-column panel staging buffer (conflict-free DMMA fragment reads)
-constexpr int POTF2_SMEM = (NB * PLD + NB * XLD + 64 + NB) * 8;
+constexpr int XLD = 12;       // pitch of the 8-column panel staging buffer (conflict-free DMMA fragment reads)
+constexpr int NT8 = NB / 8;                         // 16 tiles per block edge
+constexpr int PACKED = NT8 * (NT8 + 1) / 2 * 64;    // doubles in the packed lower triangle (136 tiles)
+constexpr int POTF2_SMEM = (PACKED + NB * XLD + 64 + NB) * 8;   // 83 KB: two CTAs per SM
+
+// The 128x128 diagonal block lives in shared memory as its lower triangle of 8x8 tiles (tile (ti,tj),
+// tj <= ti, at index ti(ti+1)/2 + tj, 64 contiguous doubles, row-major).  Inside a tile the column is
+// XOR-swizzled with bit 1 of the row, which keeps every access pattern of the kernel at the minimum
+// number of shared-memory wavefronts: DMMA C fragments (128-bit, 32 lanes = 512 contiguous bytes),
+// A fragments (row g, col q) and B fragments (row q, col g) two lanes per 8-byte bank pair.
+__device__ __forceinline__ int tile_base(int ti, int tj) { return (ti * (ti + 1) / 2 + tj) * 64; }
+__device__ __forceinline__ int in_tile(int i, int c) { return (i & 7) * 8 + ((c & 7) ^ (((i >> 1) & 1) << 2)); }
+__device__ __forceinline__ int toff(int i, int c) { return tile_base(i >> 3, c >> 3) + in_tile(i, c); }
 
 // 8x8 lower Cholesky in one thread's registers (right-looking, so the serial chain per column is
 // rsqrt -> scale -> one FMA).  a: packed lower (a[i*(i+1)/2 + j]); on exit a holds L and r[j] = 1/L_jj.
@@ -51,14 +59,15 @@ __device__ __forceinline__ int chol8(double (&a)[36], double (&r)[8]) {
 // One level of the recursive-doubling inverse on DMMA tiles:  X21 = -X22 * (L21 * X11)  for all
 // 64/S pairs of SxS diagonal blocks (X11, X22 already inverted in place, upper parts zero).
 // The contraction loop is outermost so that a warp keeps PER_WARP independent DMMA chains in flight.
-template <int S>
+// Only tiles on or below the diagonal are touched (they are the only ones stored).
+template <int S, int P2_WARPS>
 __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
   constexpr int TB = S / 8;                 // 8x8 tiles per block edge
   constexpr int TILES = (NB / (2 * S)) * TB * TB;
   constexpr int PER_WARP = (TILES + P2_WARPS - 1) / P2_WARPS;
   const int g = lane >> 2, q = lane & 3;
   double c0[PER_WARP], c1[PER_WARP];
-  int ra[PER_WARP], cb[PER_WARP], ta[PER_WARP], tb[PER_WARP], o1s[PER_WARP];
+  int ta[PER_WARP], tb[PER_WARP], t1[PER_WARP];   // tile row / column inside the pair, first tile of the pair
   bool ok[PER_WARP];
 #pragma unroll
   for (int e = 0; e < PER_WARP; e++) {
@@ -67,36 +76,41 @@ __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
     const int tt = ok[e] ? t : 0;
     const int pair = tt / (TB * TB);
     ta[e] = (tt / TB) % TB; tb[e] = tt % TB;
-    o1s[e] = pair * 2 * S;
-    ra[e] = o1s[e] + S + 8 * ta[e] + g;     // output row (in the 2-block), this lane
-    cb[e] = o1s[e] + 8 * tb[e];             // output column base
+    t1[e] = pair * 2 * TB;
     c0[e] = c1[e] = 0.0;
   }
-  // phase 1: T = L21 * X11   (X11 lower: contraction k >= 8 b)
+  const int a_in = g * 8 + (q ^ (((g >> 1) & 1) << 2));          // A fragment: row g, col q (+ k0 & 4 below)
+  // phase 1: T = L21 * X11   (X11 lower: contraction tiles kt >= b)
   for (int k0 = 0; k0 < S; k0 += 4) {
+    const int kt = k0 >> 3, kq = (k0 & 4) + q;                   // contraction tile, row/col inside it
+    const int b_in = kq * 8 + (g ^ (((kq >> 1) & 1) << 2));      // B fragment: row kq, col g
 #pragma unroll
     for (int e = 0; e < PER_WARP; e++) {
-      if (ok[e] && k0 >= 8 * tb[e]) {
-        const double af = sm[ra[e] * PLD + o1s[e] + k0 + q];
-        const double bf = sm[(o1s[e] + k0 + q) * PLD + cb[e] + g];
+      if (ok[e] && kt >= tb[e]) {
+        const double af = sm[tile_base(t1[e] + TB + ta[e], t1[e] + kt) + (a_in ^ (k0 & 4))];
+        const double bf = sm[tile_base(t1[e] + kt, t1[e] + tb[e]) + b_in];
         dmma(c0[e], c1[e], af, bf);
       }
     }
   }
   __syncthreads();
+  const int c_in = g * 8 + ((2 * q) ^ (((g >> 1) & 1) << 2));    // C fragment: row g, cols 2q, 2q+1
 #pragma unroll
   for (int e = 0; e < PER_WARP; e++) {
-    if (ok[e]) *reinterpret_cast<double2*>(sm + ra[e] * PLD + cb[e] + 2 * q) = make_double2(c0[e], c1[e]);
+    if (ok[e])
+      *reinterpret_cast<double2*>(sm + tile_base(t1[e] + TB + ta[e], t1[e] + tb[e]) + c_in) = make_double2(c0[e], c1[e]);
     c0[e] = c1[e] = 0.0;
   }
   __syncthreads();
-  // phase 2: X21 = -X22 * T   (X22 lower: contraction k < 8 a + 8)
+  // phase 2: X21 = -X22 * T   (X22 lower: contraction tiles kt <= a)
   for (int k0 = 0; k0 < S; k0 += 4) {
+    const int kt = k0 >> 3, kq = (k0 & 4) + q;
+    const int b_in = kq * 8 + (g ^ (((kq >> 1) & 1) << 2));
 #pragma unroll
     for (int e = 0; e < PER_WARP; e++) {
-      if (ok[e] && k0 < 8 * ta[e] + 8) {
-        const double af = -sm[ra[e] * PLD + o1s[e] + S + k0 + q];
-        const double bf = sm[(o1s[e] + S + k0 + q) * PLD + cb[e] + g];
+      if (ok[e] && kt <= ta[e]) {
+        const double af = -sm[tile_base(t1[e] + TB + ta[e], t1[e] + TB + kt) + (a_in ^ (k0 & 4))];
+        const double bf = sm[tile_base(t1[e] + TB + kt, t1[e] + tb[e]) + b_in];
         dmma(c0[e], c1[e], af, bf);
       }
     }
@@ -104,48 +118,37 @@ __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < PER_WARP; e++)
-    if (ok[e]) *reinterpret_cast<double2*>(sm + ra[e] * PLD + cb[e] + 2 * q) = make_double2(c0[e], c1[e]);
+    if (ok[e])
+      *reinterpret_cast<double2*>(sm + tile_base(t1[e] + TB + ta[e], t1[e] + tb[e]) + c_in) = make_double2(c0[e], c1[e]);
   __syncthreads();
 }
-
-#ifdef GPM_POTF2_TIMING
-#define PT_DECL long long pt_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_c = clock64();
-#define PT_MARK(i) { double d_ = *(volatile double*)sm; long long n_; \
-    asm volatile("mov.u64 %0, %%clock64;" : "=l"(n_) : "l"(__double_as_longlong(d_)) : "memory"); \
-    pt_t[i] += n_ - pt_c; pt_c = n_; }
-#define PT_DUMP if (blockIdx.x == 0 && threadIdx.x == 0 && kblk == 0) \
-    printf("potf2 cycles: load %lld | diag8 %lld | panel %lld | trail %lld | storeL %lld | inv %lld | storeI %lld\n", \
-           pt_t[0], pt_t[1], pt_t[2], pt_t[3], pt_t[4], pt_t[5], pt_t[6]);
-#else
-#define PT_DECL
-#define PT_MARK(i)
-#define PT_DUMP
-#endif
 
 // Factor diagonal block kblk of K in shared memory, write L_kk back and inv(L_kk) to invD.
 // Rows/columns beyond N are padded with the identity.  blockIdx.x = batch index.
 //
 // Right-looking over sixteen 8-column panels: (1) one thread factors the 8x8 diagonal block in
 // registers, (2) one thread per row forward-substitutes the panel against it, (3) all warps apply
-// the rank-8 update to the trailing 8x8 tiles with two DMMA.8x8x4 each, four tiles in flight per warp
-// (a dependent DMMA pair costs ~290 cycles).  The 128x128 inverse is then assembled from the 8x8
-// diagonal inverses by recursive doubling, also on DMMA tiles.
-__global__ void __launch_bounds__(P2_THREADS, 1)
+// the rank-8 update to the trailing 8x8 tiles with DMMA.8x8x4 on a static balanced schedule.  The
+// 128x128 inverse is then assembled from the 8x8 diagonal inverses by recursive doubling, also on
+// DMMA tiles.  The kernel is latency-bound (serial pivot chain, barrier hand-offs), so it is sized
+// for two CTAs per SM (83 KB shared memory, 256 threads): batched fits keep both busy.
+template <int P2_THREADS>
+__global__ void __launch_bounds__(P2_THREADS, 512 / P2_THREADS)
 potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, double* __restrict__ invD,
                  int* __restrict__ info, long long batch_k, long long batch_inv) {
-  extern __shared__ double sm[];
-  double* xp = sm + NB * PLD;          // [128][XLD] current panel
+  extern __shared__ __align__(16) double sm[];
+  double* xp = sm + PACKED;            // [128][XLD] current panel
   double* l8 = xp + NB * XLD;          // [36] current 8x8 factor (packed lower)
   double* rd = l8 + 64;                // [128] reciprocals of the diagonal of L
+  constexpr int P2_WARPS = P2_THREADS / 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   K += blockIdx.x * batch_k;
   invD += blockIdx.x * batch_inv + (long long)kblk * NB * NB;
   info += blockIdx.x;
   const long long r0 = (long long)kblk * NB;
   const int nv = (int)((N - r0) < NB ? (N - r0) : NB);
-  PT_DECL
 
-  // load (16 independent loads in flight per thread)
+  // load the lower triangle (16 independent loads in flight per thread); identity padding beyond nv
   for (int u0 = 0; u0 < NB * NB / P2_THREADS; u0 += 16) {
     double v[16];
 #pragma unroll
@@ -156,23 +159,24 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
     }
 #pragma unroll
     for (int u = 0; u < 16; u++) {
-      const int idx = tid + P2_THREADS * (u0 + u);
-      sm[(idx >> 7) * PLD + (idx & 127)] = v[u];
+      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 7, c = idx & 127;
+      if ((c >> 3) <= (i >> 3)) sm[toff(i, c)] = v[u];
     }
   }
   __syncthreads();
-  PT_MARK(0)
 
   const int g = lane >> 2, q = lane & 3;
+  const int c_in = g * 8 + ((2 * q) ^ (((g >> 1) & 1) << 2));
   for (int p = 0; p < 16; p++) {
     const int c0 = 8 * p;
     // (1) 8x8 diagonal block: factor in one thread
     if (tid == 0) {
       double a[36], r[8];
+      const int tb0 = tile_base(p, p);
 #pragma unroll
       for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j <= i; j++) a[i * (i + 1) / 2 + j] = sm[(c0 + i) * PLD + c0 + j];
+        for (int j = 0; j <= i; j++) a[i * (i + 1) / 2 + j] = sm[tb0 + in_tile(i, j)];
       const int bad = chol8(a, r);
       if (bad && c0 + bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + c0 + bad));
 #pragma unroll
@@ -180,49 +184,44 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
         rd[c0 + i] = r[i];
 #pragma unroll
         for (int j = 0; j <= i; j++) {
-          sm[(c0 + i) * PLD + c0 + j] = a[i * (i + 1) / 2 + j];
+          sm[tb0 + in_tile(i, j)] = a[i * (i + 1) / 2 + j];
           l8[i * (i + 1) / 2 + j] = a[i * (i + 1) / 2 + j];
         }
       }
     }
     __syncthreads();
-    PT_MARK(1)
     // (2) panel solve by forward substitution, one thread per row below the block:
     //     x_c = (a_c - sum_{k<c} x_k L8[c][k]) / L8[c][c]
     if (tid < NB && tid >= c0 + 8) {
       double x[8];
-      double* row = sm + tid * PLD + c0;
+      double* row = sm + tile_base(tid >> 3, p) + (tid & 7) * 8;
+      const int sw = ((tid >> 1) & 1) << 2;
 #pragma unroll
       for (int c = 0; c < 8; c++) {
-        double v = row[c];
+        double v = row[c ^ sw];
 #pragma unroll
         for (int k = 0; k < 8; k++)
           if (k < c) v = fma(-x[k], l8[c * (c + 1) / 2 + k], v);
         x[c] = v * rd[c0 + c];
       }
 #pragma unroll
-      for (int c = 0; c < 8; c++) { row[c] = x[c]; xp[tid * XLD + c] = x[c]; }
+      for (int c = 0; c < 8; c++) { row[c ^ sw] = x[c]; xp[tid * XLD + c] = x[c]; }
     }
     __syncthreads();
-    PT_MARK(2)
-    // (3) trailing update on 8x8 tiles: C[ti][tj] -= X_ti X_tj^T; four independent tiles per iteration
-    const int nt = 15 - p, rb = c0 + 8;
-    const int ntiles = nt * (nt + 1) / 2;
-    // balanced static schedule: tile-rows a and b = nt-1-a together hold nt+1 tiles; warps 2a and 2a+1
-    // each take half of that run, so no warp does more than ceil((nt+1)/2) tiles and there is no
-    // per-tile index search.  The A fragment (rows of tile-row ti) stays in registers along a row.
+    // (3) trailing update on 8x8 tiles: C[ti][tj] -= X_ti X_tj^T.  Balanced static schedule: tile-rows a and
+    // b = nt-1-a together hold nt+1 tiles (nt <= 15 -> at most 8 pairs); with 8 warps each warp takes one pair,
+    // with 16 warps two warps share a pair.
+    const int nt = 15 - p, rb = c0 + 8, rbt = p + 1;
     {
-      const int a_row = warp >> 1, b_row = nt - 1 - a_row;
+      const int a_row = P2_WARPS == 8 ? warp : warp >> 1, b_row = nt - 1 - a_row;
       if (a_row <= b_row) {
         const int na = a_row + 1;
-        const int total = (a_row == b_row) ? na : nt + 1;
-        const int halfn = (total + 1) >> 1;
-        const int pos0 = (warp & 1) * halfn;
-        const int pos1 = min(total, pos0 + halfn);
-        // DMMA.8x8x4 latency is ~130 cycles: keep four independent DMMAs in flight (two tiles, each
-        // with its two k-halves in separate accumulators) instead of dependent pairs.
-        for (int pos = pos0; pos < pos1; pos += 2) {
-          const bool two = pos + 1 < pos1;
+        const int run = (a_row == b_row) ? na : nt + 1;
+        const int halfn = P2_WARPS == 8 ? run : (run + 1) >> 1;
+        const int pos0 = P2_WARPS == 8 ? 0 : (warp & 1) * halfn;
+        const int total = min(run, pos0 + halfn);
+        for (int pos = pos0; pos < total; pos += 2) {
+          const bool two = pos + 1 < total;
           const int pb_ = two ? pos + 1 : pos;
           const int ti0 = pos < na ? a_row : b_row, tj0 = pos < na ? pos : pos - na;
           const int ti1 = pb_ < na ? a_row : b_row, tj1 = pb_ < na ? pb_ : pb_ - na;
@@ -230,8 +229,8 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
           const double* xa_1 = xp + (rb + 8 * ti1 + g) * XLD + q;
           const double* xb_0 = xp + (rb + 8 * tj0 + g) * XLD + q;
           const double* xb_1 = xp + (rb + 8 * tj1 + g) * XLD + q;
-          double2* cp0 = reinterpret_cast<double2*>(sm + (rb + 8 * ti0 + g) * PLD + rb + 8 * tj0 + 2 * q);
-          double2* cp1 = reinterpret_cast<double2*>(sm + (rb + 8 * ti1 + g) * PLD + rb + 8 * tj1 + 2 * q);
+          double2* cp0 = reinterpret_cast<double2*>(sm + tile_base(rbt + ti0, rbt + tj0) + c_in);
+          double2* cp1 = reinterpret_cast<double2*>(sm + tile_base(rbt + ti1, rbt + tj1) + c_in);
           const double a00 = -xa_0[0], a01 = -xa_0[4], a10 = -xa_1[0], a11 = -xa_1[4];
           const double b00 = xb_0[0], b01 = xb_0[4], b10 = xb_1[0], b11 = xb_1[4];
           double2 c0v = *cp0, c1v = *cp1;
@@ -247,7 +246,6 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
       }
     }
     __syncthreads();
-    PT_MARK(3)
   }
 
   // ---- write L_kk (lower part, valid rows) ----
@@ -255,53 +253,45 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
 #pragma unroll
     for (int u = 0; u < 16; u++) {
       const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 7, c = idx & 127;
-      if (c <= i && i < nv) K[(r0 + i) * ldk + r0 + c] = sm[i * PLD + c];
+      if (c <= i && i < nv) K[(r0 + i) * ldk + r0 + c] = sm[toff(i, c)];
     }
   }
   // ---- inverse, level 0: the sixteen 8x8 diagonal blocks, one thread per column ----
   double xcol[8];
   {
-    const int pb = (tid >> 3) * 8, j = tid & 7;
+    const int pt = tid >> 3, j = tid & 7;
     if (tid < NB) {
-      const double* Lb = sm + pb * PLD + pb;
+      const double* Lb = sm + tile_base(pt, pt);
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         double v = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; k++)
-          if (k < i) v = fma(Lb[i * PLD + k], (k >= j) ? xcol[k] : 0.0, v);
-        xcol[i] = (i < j) ? 0.0 : ((i == j) ? rd[pb + i] : -v * rd[pb + i]);
+          if (k < i) v = fma(Lb[in_tile(i, k)], (k >= j) ? xcol[k] : 0.0, v);
+        xcol[i] = (i < j) ? 0.0 : ((i == j) ? rd[pt * 8 + i] : -v * rd[pt * 8 + i]);
       }
     }
   }
   __syncthreads();
-  // clear the strict upper triangle (the diagonal-tile updates wrote symmetric garbage there)
-  for (int idx = tid; idx < NB * NB; idx += P2_THREADS) {
-    const int i = idx >> 7, c = idx & 127;
-    if (c > i) sm[i * PLD + c] = 0.0;
-  }
-  if (tid < NB) {
-    const int pb = (tid >> 3) * 8, j = tid & 7;
+  if (tid < NB) {       // each column of each diagonal tile gets its inverse (zeros above the diagonal)
+    const int pt = tid >> 3, j = tid & 7;
+    double* Lb = sm + tile_base(pt, pt);
 #pragma unroll
-    for (int i = 0; i < 8; i++) sm[(pb + i) * PLD + pb + j] = xcol[i];
+    for (int i = 0; i < 8; i++) Lb[in_tile(i, j)] = xcol[i];
   }
   __syncthreads();
-  PT_MARK(4)
-  inv_level_dmma<8>(sm, warp, lane);
-  inv_level_dmma<16>(sm, warp, lane);
-  inv_level_dmma<32>(sm, warp, lane);
-  inv_level_dmma<64>(sm, warp, lane);
-  PT_MARK(5)
+  inv_level_dmma<8, P2_WARPS>(sm, warp, lane);
+  inv_level_dmma<16, P2_WARPS>(sm, warp, lane);
+  inv_level_dmma<32, P2_WARPS>(sm, warp, lane);
+  inv_level_dmma<64, P2_WARPS>(sm, warp, lane);
 
   for (int u0 = 0; u0 < NB * NB / P2_THREADS; u0 += 16) {
 #pragma unroll
     for (int u = 0; u < 16; u++) {
-      const int idx = tid + P2_THREADS * (u0 + u);
-      invD[idx] = sm[(idx >> 7) * PLD + (idx & 127)];
+      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 7, c = idx & 127;
+      invD[idx] = ((c >> 3) <= (i >> 3)) ? sm[toff(i, c)] : 0.0;
     }
   }
-  PT_MARK(6)
-  PT_DUMP
 }
 
 __global__ void zero_info_kernel(int* info, int n) {
@@ -313,10 +303,16 @@ int launch_potf2(double* K, long long ldk, long long N, int kblk, double* invD, 
                  long long batch_k, long long batch_inv, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    GPM_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
+    GPM_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
+    GPM_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    GPM_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
     attr_set = true;
   }
-  potf2_inv_kernel<<<batch, P2_THREADS, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv);
+  // a lone block is latency-critical (16 warps); batches are throughput-bound (8 warps, two CTAs per SM)
+  if (batch >= 64)
+    potf2_inv_kernel<256><<<batch, 256, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv);
+  else
+    potf2_inv_kernel<512><<<batch, 512, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv);
   GPM_LAUNCH_CHECK();
   return 0;
 }
