@@ -384,6 +384,24 @@ def run_b200(args):
         m1 = GPmap.fit_gp(X1d, Y1d, theta=th1, check=False)
         return m1.predict_grid(wl.BOX, (100, 100))
     extra["cfg1_N200_100x100_latency_ms"] = timed(torch, cfg1, 20, warm=3)
+    # the same step captured once into a CUDA graph and replayed (launch-bound case)
+    try:
+        mu_e, var_e = cfg1()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                cfg1()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            mu_g, var_g = cfg1()
+        graph.replay(); torch.cuda.synchronize()
+        same = bool(torch.equal(mu_g, mu_e) and torch.equal(var_g, var_e))
+        extra["cfg1_cuda_graph_latency_ms"] = timed(torch, graph.replay, 50, warm=3)
+        extra["cfg1_cuda_graph_matches_eager"] = same
+    except Exception as e:                                   # noqa: BLE001
+        extra["cfg1_cuda_graph_error"] = str(e)[:200]
 
     # ---- the other two headline numbers: Cholesky TFLOP/s at N=16384, batched fits/s ---------------
     if not args.no_extra:

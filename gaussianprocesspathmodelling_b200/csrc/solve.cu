@@ -334,8 +334,11 @@ int solve_chain(gpm_handle_impl* h, const double* L, long long N, long long ldl,
   int nblk = (int)((N + NB - 1) / NB);
   if (nblk > h->n_flags) { set_error("solve: N too large for the handle's flag arrays"); return 997; }
   int grid = nblk < h->sm_count ? nblk : h->sm_count;
+  // flags are cleared on the stream before each direction (constant epoch), so the call sequence can be
+  // captured into a CUDA graph and replayed
+  GPM_CUDA(cudaMemsetAsync(h->flags, 0, 2 * (size_t)h->n_flags * sizeof(int), stream));
   for (int dir = 0; dir < 2; dir++) {
-    int epoch = ++h->epoch;
+    int epoch = 1;
     int* flags = h->flags + dir * h->n_flags;
     void* args[] = {(void*)&L, (void*)&ldl, (void*)&N, (void*)&invD, (void*)&alpha, (void*)&R, (void*)&nblk,
                     (void*)&flags, (void*)&epoch};
