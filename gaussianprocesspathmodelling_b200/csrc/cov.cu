@@ -75,7 +75,7 @@ cross_cov_t_kernel(const double* __restrict__ X, long long N, Theta th, const do
                    long long ldks, long long ncols_pad) {
   __shared__ double q[32][3];
   const int tid = threadIdx.x;
-  const long long mb = (long long)blockIdx.y * 32;
+  const long long mb = (long long)blockIdx.x * 32;          // row blocks in x: up to 2^31-1 of them
   if (tid < 32) {
     const long long m = mb + tid;
     double c[3] = {0.0, 0.0, 0.0};
@@ -87,7 +87,7 @@ cross_cov_t_kernel(const double* __restrict__ X, long long N, Theta th, const do
     for (int d = 0; d < D; d++) q[tid][d] = c[d] / th.l[d];
   }
   __syncthreads();
-  const long long i = (long long)blockIdx.x * 256 + tid;
+  const long long i = (long long)blockIdx.y * 256 + tid;
   if (i >= ncols_pad) return;
   double xi[3] = {0.0, 0.0, 0.0};
   if (i < N) {
@@ -162,7 +162,7 @@ int launch_cross_cov_t(const double* X, long long N, int D, const Theta& th, con
   gpm_grid_t g = {};
   if (grid) g = *grid;
   const int use_grid = Xs == nullptr;
-  dim3 gridDim((unsigned)((ncols_pad + 255) / 256), (unsigned)((M + 31) / 32));
+  dim3 gridDim((unsigned)((M + 31) / 32), (unsigned)((ncols_pad + 255) / 256));
   if (D == 2) cross_cov_t_kernel<2><<<gridDim, 256, 0, stream>>>(X, N, th, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad);
   else cross_cov_t_kernel<3><<<gridDim, 256, 0, stream>>>(X, N, th, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad);
   GPM_LAUNCH_CHECK();

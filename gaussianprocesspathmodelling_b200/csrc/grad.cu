@@ -14,8 +14,8 @@ constexpr int GMAXR = 8;
 constexpr int GACC = 4 * (1 + GMAXR);   // (D+1 <= 4 kernel terms) x (trace + R quadratic forms)
 
 __global__ void identity_kernel(double* __restrict__ W, long long N, long long ld, long long rows) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long m = blockIdx.y;
+  const long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x;
+  const long long m = blockIdx.x;
   if (i < ld && m < rows) W[m * ld + i] = (i == m && m < N) ? 1.0 : 0.0;
 }
 
@@ -159,7 +159,7 @@ extern "C" int gpm_lml_grad(gpm_handle_t handle, const double* X, int64_t N, int
   if ((rc = make_tmap(h, &mapKi, Kinv, np, np, np, NB))) return rc;
 
   // W = I, then W <- W L^{-T} = L^{-T} (block upper triangular: row block t starts at block column t)
-  dim3 gi((unsigned)((np + 255) / 256), (unsigned)np);
+  dim3 gi((unsigned)np, (unsigned)((np + 255) / 256));
   identity_kernel<<<gi, 256, 0, st>>>(W, N, np, np);
   GPM_LAUNCH_CHECK();
   GPM_CUDA(cudaMemsetAsync(rowsq, 0, (size_t)np * sizeof(double), st));

@@ -426,3 +426,17 @@ def test_cuda_graph_capture_replays_bitwise():
     graph.replay(); torch.cuda.synchronize()
     mo = gp_ref.fit(X, Y2, th)
     assert nrm(out[2].cpu().numpy(), mo["alpha"]) < MEAN_TOL
+
+
+def test_many_query_points_small_model():
+    # 2.2 M query points in one chunk for a tiny model: more than 65535 row blocks in one launch
+    X, Y, th = wl.single_path(64, seed=33, D=2, R=1)
+    m = GPmap.fit_gp(X, Y, theta=th)
+    mu, var = m.predict_grid(wl.BOX, (1500, 1480))
+    mo = gp_ref.fit(X, Y, th)
+    idx = np.arange(0, 1500 * 1480, 4099)
+    P = gp_ref.grid_points(wl.BOX, (1500, 1480))[idx]
+    mu_o, var_o = gp_ref.predict(mo, P)
+    assert nrm(mu.view(-1, 1)[idx].cpu().numpy(), mu_o) < MEAN_TOL
+    assert nrm(var.view(-1)[idx].cpu().numpy(), var_o) < VAR_TOL
+    assert bool(torch.isfinite(var).all())
