@@ -56,13 +56,17 @@ __device__ __forceinline__ OpDesc make_op(const GemmArgs& p, const TileCoord& tc
     d.second_b = !isU;
     d.rowsq = !isU;
   } else {
-    const int skip = (p.tri && p.tri_kstart) ? tc.ti * NB : 0;
-    d.nslab = (p.klen - skip) / SLAB_K;
-    d.a_col0 = p.a_col0 + skip;
-    d.b_col0 = p.b_col0 + skip;
+    const int lo = p.kstart_mode == 1 ? tc.ti * NB : 0;
+    int hi = p.klen;
+    if (p.kend_mode == 1) hi = min(hi, (tc.ti + 1) * NB);
+    if (p.kend_mode == 2) hi = min(hi, (tc.tj + 1) * NB);
+    const int bcol = (int)(bz * p.batch_cols);
+    d.nslab = (hi - lo) / SLAB_K;
+    d.a_col0 = p.a_col0 + lo + bcol;
+    d.b_col0 = p.b_col0 + lo + bcol;
     d.b_row = p.b_row0 + tc.tj * p.b_tile_rows + (int)(bz * p.batch_b_rows);
     d.epi = p.epi;
-    d.c_col = p.c_col0 + (long long)tc.tj * NB;
+    d.c_col = p.c_col0 + (long long)tc.tj * NB + bz * p.batch_cols;
     d.second_b = false;
     d.rowsq = p.rowsq != nullptr;
   }
@@ -217,6 +221,12 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) mbar_arrive(bar_cempty);
         ct++;
       }
+      if (d.epi == EPI_NEG) {
+#pragma unroll
+        for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) { acc[mt][nt][0] = -acc[mt][nt][0]; acc[mt][nt][1] = -acc[mt][nt][1]; }
+      }
 #pragma unroll
       for (int mt = 0; mt < 8; mt++) {
         const long long row = crow_base + mt * 8 + g;
@@ -297,7 +307,7 @@ int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& 
     const long long span = ((ctas + slots - 1) / slots) * c;
     if (best_span < 0 || span <= best_span) { best_span = span; best_c = c; }
   }
-  if (args.sweep_tri || args.tri_kstart) best_c = 1;   // tiles differ in work: let the hardware balance them
+  if (args.sweep_tri || args.kstart_mode || args.kend_mode) best_c = 1;   // tiles differ in work: let the hardware balance them
   args.tiles_per_cta = best_c;
   dim3 grid(args.sweep_tri ? (total + 1) / 2 : (total + best_c - 1) / best_c, batch);
   gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(mapA, mapB, mapC, mapB2 ? *mapB2 : mapB, args);

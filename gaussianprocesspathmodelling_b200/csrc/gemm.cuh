@@ -6,7 +6,7 @@
 
 namespace gpm {
 
-enum { EPI_STORE = 0, EPI_SUB = 1 };
+enum { EPI_STORE = 0, EPI_SUB = 1, EPI_NEG = 2 };   // C = acc;  C = C - acc;  C = -acc
 
 struct GemmArgs {
   double* C;              // output matrix
@@ -32,7 +32,10 @@ struct GemmArgs {
   int sweep_nblk;
   int sweep_tri;          // sweep mode on a block-upper-triangular right-hand side (row block t is zero left of
                           // block column t): row block t starts at op D(t) and contracts from column t*NB
-  int tri_kstart;         // tile mode, tri != 0: operands are zero left of block column ti -> contract from ti*NB
+  // tile mode: triangular operands let a tile skip the structurally-zero part of the contraction
+  int kstart_mode;        // 1: start at ti*NB (A zero left of its diagonal block)
+  int kend_mode;          // 1: stop at (ti+1)*NB (A zero right of its diagonal block); 2: stop at (tj+1)*NB (same for B)
+  long long batch_cols;   // columns added per batch index to the A, B and C column origins
   int tiles_per_cta;      // filled by launch_gemm: consecutive tiles one CTA works through
   int max_tiles_per_cta;  // 0 = default (16); the look-ahead Cholesky caps it so that SMs free up regularly
 };

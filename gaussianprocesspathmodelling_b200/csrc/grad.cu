@@ -5,6 +5,10 @@
 // K^{-1} = W W^T as a lower-triangular tile SYRK that contracts from the first non-zero block
 // (another N^3/3).  One fused pass over K^{-1} then evaluates the kernel derivatives on the fly
 // (distance + exp, like the covariance kernel) and reduces all D+2 traces and quadratic forms.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "gemm.cuh"
 
 namespace gpm {
@@ -17,6 +21,23 @@ __global__ void identity_kernel(double* __restrict__ W, long long N, long long l
   const long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x;
   const long long m = blockIdx.x;
   if (i < ld && m < rows) W[m * ld + i] = (i == m && m < N) ? 1.0 : 0.0;
+}
+
+// X (lower) and U (upper) start as the inverted diagonal blocks and their transposes.
+__global__ void __launch_bounds__(256)
+place_diag_kernel(const double* __restrict__ invD, double* __restrict__ Xm, double* __restrict__ Um, long long ld) {
+  __shared__ double t[32][33];
+  const int k = blockIdx.z, bi = blockIdx.y * 32, bj = blockIdx.x * 32;
+  const double* D = invD + (long long)k * NB * NB;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long o = (long long)k * NB;
+  for (int r = ty; r < 32; r += 8) {
+    const double v = D[(bi + r) * NB + bj + tx];
+    t[r][tx] = v;
+    Xm[(o + bi + r) * ld + o + bj + tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) Um[(o + bj + r) * ld + o + bi + tx] = t[tx][r];
 }
 
 // partial[cta][j*(1+R) + 0]     = sum_ab w * Kinv_ab * dKf_j(a,b)            (j < D: lengthscale d, j = D: signal_var)
@@ -124,7 +145,7 @@ extern "C" size_t gpm_lml_grad_workspace_bytes(int64_t N) {
   if (N <= 0) return 0;
   const long long np = round_up_g(N, NB);
   const long long t = (N + GT - 1) / GT;
-  return (size_t)(2 * np * np + np + t * (t + 1) / 2 * (GACC + 1 + GMAXR)) * sizeof(double);
+  return (size_t)(3 * np * np + np + t * (t + 1) / 2 * (GACC + 1 + GMAXR)) * sizeof(double);
 }
 
 extern "C" int gpm_lml_grad(gpm_handle_t handle, const double* X, int64_t N, int32_t D, const double* theta,
@@ -148,8 +169,8 @@ extern "C" int gpm_lml_grad(gpm_handle_t handle, const double* X, int64_t N, int
   const long long np = round_up_g(N, NB);
   const int nblk = (int)(np / NB);
   double* W = reinterpret_cast<double*>(ws);
-  double* Kinv = W + np * np;
-  double* rowsq = Kinv + np * np;
+  double* Kinv = W + np * np;              // also holds X = L^{-1} during the recursion
+  double* rowsq = Kinv + 2 * np * np;      // [Kinv | T] then rowsq, partial
   double* partial = rowsq + np;
   CUtensorMap mapW, mapL, mapInv, mapKi;
   int rc;
@@ -158,21 +179,72 @@ extern "C" int gpm_lml_grad(gpm_handle_t handle, const double* X, int64_t N, int
   if ((rc = make_tmap(h, &mapInv, reinterpret_cast<const double*>(potrf_ws), (long long)nblk * NB, NB, NB, NB))) return rc;
   if ((rc = make_tmap(h, &mapKi, Kinv, np, np, np, NB))) return rc;
 
-  // W = I, then W <- W L^{-T} = L^{-T} (block upper triangular: row block t starts at block column t)
-  dim3 gi((unsigned)np, (unsigned)((np + 255) / 256));
-  identity_kernel<<<gi, 256, 0, st>>>(W, N, np, np);
-  GPM_LAUNCH_CHECK();
-  GPM_CUDA(cudaMemsetAsync(rowsq, 0, (size_t)np * sizeof(double), st));
-  GemmArgs a = {};
-  a.C = W; a.ldc = np; a.rowsq = rowsq;
-  a.tiles_m = nblk; a.tiles_n = 1; a.tri = 0;
-  a.c_row0 = 0; a.c_rows_end = np; a.c_cols_end = np;
-  a.sweep_nblk = nblk; a.sweep_tri = 1; a.epi = EPI_STORE; a.klen = NB;
-  if ((rc = launch_gemm(h, mapW, mapL, mapW, a, 1, st, &mapInv))) return rc;
+  if (getenv("GPM_GRAD_SWEEP")) {
+    // reference path: W = I, then W <- W L^{-T} by the triangular sweep (row block 0 is a long serial chain)
+    dim3 gi((unsigned)np, (unsigned)((np + 255) / 256));
+    identity_kernel<<<gi, 256, 0, st>>>(W, N, np, np);
+    GPM_LAUNCH_CHECK();
+    GPM_CUDA(cudaMemsetAsync(rowsq, 0, (size_t)np * sizeof(double), st));
+    GemmArgs a = {};
+    a.C = W; a.ldc = np; a.rowsq = rowsq;
+    a.tiles_m = nblk; a.tiles_n = 1; a.tri = 0;
+    a.c_row0 = 0; a.c_rows_end = np; a.c_cols_end = np;
+    a.sweep_nblk = nblk; a.sweep_tri = 1; a.epi = EPI_STORE; a.klen = NB;
+    if ((rc = launch_gemm(h, mapW, mapL, mapW, a, 1, st, &mapInv))) return rc;
+  } else {
+    // Recursive doubling: for blocks of size ns = 128, 256, ... and each pair (1, 2) of adjacent blocks
+    //   T   = U11 L21^T            X21 = -X22 T^T            U12 = -T X22^T
+    // with X = L^{-1} (lower) and U = L^{-T} (upper) both kept, so that every product is an NT GEMM with
+    // the contraction index contiguous; triangular operands skip their zero halves per tile.  All pairs of a
+    // level run in one batched launch: N^3/2 flops in fully parallel launches.  U ends up in W.
+    double* Xm = Kinv;                       // K^{-1} is formed afterwards, so its storage holds X until then
+    double* Tm = Xm + np * np;               // (workspace sized for it)
+    CUtensorMap mapX, mapT;
+    if ((rc = make_tmap(h, &mapX, Xm, np, np, np, NB))) return rc;
+    if ((rc = make_tmap(h, &mapT, Tm, np, np, np, NB))) return rc;
+    GPM_CUDA(cudaMemsetAsync(W, 0, (size_t)np * np * sizeof(double), st));
+    GPM_CUDA(cudaMemsetAsync(Xm, 0, (size_t)np * np * sizeof(double), st));
+    place_diag_kernel<<<dim3(4, 4, nblk), 256, 0, st>>>(reinterpret_cast<const double*>(potrf_ws), Xm, W, np);
+    GPM_LAUNCH_CHECK();
+    for (long long ns = NB; ns < np; ns *= 2) {
+      const long long nb_s = (np + ns - 1) / ns;
+      const int pairs = (int)(nb_s / 2);
+      const long long n2_last = std::min(ns, np - ((long long)(2 * pairs - 1) * ns));
+      const int full = (n2_last == ns) ? pairs : pairs - 1;
+      for (int pass = 0; pass < 2; pass++) {          // pass 0: the full-size pairs (batched); pass 1: a ragged last pair
+        const int batch = pass == 0 ? full : (pairs - full);
+        if (batch <= 0) continue;
+        const long long o1 = pass == 0 ? 0 : (long long)(2 * full) * ns, o2 = o1 + ns;
+        const long long n2 = pass == 0 ? ns : n2_last;
+        const int t1 = (int)(ns / NB), t2 = (int)(n2 / NB);
+        GemmArgs g = {};
+        g.batch_a_rows = g.batch_b_rows = g.batch_c_rows = 2 * ns; g.batch_cols = 2 * ns;
+        g.b_tile_rows = NB; g.tri = 0; g.rowsq = nullptr;
+        // T[a][c] = sum_i U11[a][i] L21[c][i]          (U11 upper: contract from the tile's own block on)
+        g.C = Tm; g.ldc = np; g.tiles_m = t1; g.tiles_n = t2;
+        g.a_row0 = (int)o1; g.a_col0 = (int)o1; g.b_row0 = (int)o2; g.b_col0 = (int)o1; g.klen = (int)ns;
+        g.c_row0 = o1; g.c_col0 = o2; g.c_rows_end = np; g.c_cols_end = np;
+        g.epi = EPI_STORE; g.kstart_mode = 1; g.kend_mode = 0;
+        if ((rc = launch_gemm(h, mapW, mapL, mapT, g, batch, st))) return rc;
+        // X21[b][a] = -sum_c X22[b][c] T[a][c]         (X22 lower: contract up to the tile's own block)
+        g.C = Xm; g.tiles_m = t2; g.tiles_n = t1;
+        g.a_row0 = (int)o2; g.a_col0 = (int)o2; g.b_row0 = (int)o1; g.b_col0 = (int)o2; g.klen = (int)n2;
+        g.c_row0 = o2; g.c_col0 = o1;
+        g.epi = EPI_NEG; g.kstart_mode = 0; g.kend_mode = 1;
+        if ((rc = launch_gemm(h, mapX, mapT, mapX, g, batch, st))) return rc;
+        // U12[a][b] = -sum_c T[a][c] X22[b][c]
+        g.C = W; g.tiles_m = t1; g.tiles_n = t2;
+        g.a_row0 = (int)o1; g.a_col0 = (int)o2; g.b_row0 = (int)o2; g.b_col0 = (int)o2; g.klen = (int)n2;
+        g.c_row0 = o1; g.c_col0 = o2;
+        g.epi = EPI_NEG; g.kstart_mode = 0; g.kend_mode = 2;
+        if ((rc = launch_gemm(h, mapT, mapX, mapW, g, batch, st))) return rc;
+      }
+    }
+  }
   // K^{-1} = W W^T on the tiles on/below the diagonal, contracting from the first non-zero block column
   GemmArgs s = {};
   s.C = Kinv; s.ldc = np; s.rowsq = nullptr;
-  s.tri = 1; s.tiles_m = nblk; s.tiles_n = nblk; s.tri_kstart = 1;
+  s.tri = 1; s.tiles_m = nblk; s.tiles_n = nblk; s.kstart_mode = 1;
   s.a_row0 = 0; s.b_row0 = 0; s.a_col0 = 0; s.b_col0 = 0; s.b_tile_rows = NB; s.klen = (int)np;
   s.c_row0 = 0; s.c_col0 = 0; s.c_rows_end = np; s.c_cols_end = np;
   s.epi = EPI_STORE;
