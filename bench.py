@@ -51,13 +51,13 @@ def load_peaks():
 
 
 def ncu_traffic():
-    """DRAM bytes (read + write) of the dominant kernel from the committed ncu capture (deep-K update launch)."""
+    """DRAM bytes (read + write) of the dominant launch -- the fused variance sweep of gemm_nt_kernel -- from the
+    committed `ncu --set full` capture of the same workload (profiles/r01_final_ncu_gemm_summary.json)."""
     try:
-        s = json.load(open(os.path.join(ROOT, "profiles", "r01_v4_ncu_gemm_summary.json")))
-        l = s["launches"][1]
-        return {"bytes_per_launch": l["dram_read_bytes"] + l["dram_write_bytes"], "launch": l["role"],
-                "algorithmic_operand_bytes": l["algorithmic_operand_bytes"], "duration_ms": l["duration_ms"],
-                "dmma_pipe_active_pct": l["dmma_pipe_active_pct"], "source": "profiles/r01_v4_ncu_gemm_summary.json"}
+        s = json.load(open(os.path.join(ROOT, "profiles", "r01_final_ncu_gemm_summary.json")))
+        return {"bytes_per_launch": s["dram_read_bytes"] + s["dram_write_bytes"],
+                "algorithmic_operand_bytes": s["algorithmic_operand_bytes"], "duration_ms_under_ncu": s["duration_ms"],
+                "dmma_pipe_active_pct": s["dmma_pipe_active_pct"], "source": "profiles/r01_final_ncu_gemm_summary.json"}
     except Exception:
         return None
 
@@ -356,7 +356,7 @@ def run_b200(args):
     var_flops = float(N) * N * M_local
     var_tflops = var_flops / (phases["predict_var_ms"] * 1e-3) / 1e12
     roofline = {
-        "kernel": "gemm_nt_kernel (DMMA.8x8x4 + TMA) inside the blocked TRSM of the posterior variance",
+        "kernel": "gemm_nt_kernel (DMMA.8x8x4 + TMA): the fused blocked-TRSM sweep of the posterior variance, one persistent launch",
         "bound": "tensor", "achieved": var_tflops, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
         "frac": var_tflops / peaks["fp64_tflops"], "traffic": ncu_traffic(),
         "peak_source": peaks["fp64_src"],
