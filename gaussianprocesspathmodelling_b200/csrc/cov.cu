@@ -104,6 +104,79 @@ cross_cov_t_kernel(const double* __restrict__ X, long long N, Theta th, const do
   }
 }
 
+// Fused cross-covariance + posterior mean (used when the variance is wanted too, so K*^T has to be
+// materialised anyway): a CTA owns 8 query rows and walks all training columns, 256 at a time; every
+// k(xs_m, x_i) is evaluated once, stored to KsT (coalesced 2 KB row segments) and accumulated into the
+// mean; the 8 x R partial sums are reduced across the CTA at the end (fixed order: deterministic).
+template <int D, int RR>
+__global__ void __launch_bounds__(256)
+cross_cov_mean_kernel(const double* __restrict__ X, long long N, Theta th, const double* __restrict__ alpha, int R,
+                      const double* __restrict__ Xs, gpm_grid_t grid, int use_grid, long long m0, long long M,
+                      double* __restrict__ KsT, long long ldks, long long ncols_pad, double* __restrict__ mu) {
+  constexpr int QR = 8;
+  __shared__ double q[QR][3];
+  __shared__ double red[8][QR * RR];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long mb = (long long)blockIdx.x * QR;
+  if (tid < QR) {
+    const long long m = mb + tid;
+    double c[3] = {0.0, 0.0, 0.0};
+    if (m < M) {
+      if (use_grid) { grid_point(grid, m0 + m, c[0], c[1]); c[2] = grid.t; }
+      else { for (int d = 0; d < D; d++) c[d] = Xs[(m0 + m) * D + d]; }
+    }
+#pragma unroll
+    for (int d = 0; d < D; d++) q[tid][d] = c[d] / th.l[d];
+  }
+  __syncthreads();
+  double qr[QR][3];
+#pragma unroll
+  for (int r = 0; r < QR; r++)
+#pragma unroll
+    for (int d = 0; d < D; d++) qr[r][d] = q[r][d];
+  double acc[QR][RR];
+#pragma unroll
+  for (int r = 0; r < QR; r++)
+#pragma unroll
+    for (int k = 0; k < RR; k++) acc[r][k] = 0.0;
+  for (long long i = tid; i < ncols_pad; i += 256) {
+    double xi[3] = {0.0, 0.0, 0.0}, a[RR];
+#pragma unroll
+    for (int k = 0; k < RR; k++) a[k] = 0.0;
+    const bool in = i < N;
+    if (in) {
+#pragma unroll
+      for (int d = 0; d < D; d++) xi[d] = X[i * D + d] / th.l[d];
+#pragma unroll
+      for (int k = 0; k < RR; k++) if (k < R) a[k] = alpha[i * R + k];
+    }
+#pragma unroll
+    for (int r = 0; r < QR; r++) {
+      if (mb + r < M) {
+        const double v = in ? rbf<D>(qr[r], xi, th.sf2) : 0.0;
+        KsT[(mb + r) * ldks + i] = v;
+#pragma unroll
+        for (int k = 0; k < RR; k++) acc[r][k] = fma(v, a[k], acc[r][k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < QR; r++)
+#pragma unroll
+    for (int k = 0; k < RR; k++) {
+      const double sv = warp_sum(acc[r][k]);
+      if (lane == 0) red[warp][r * RR + k] = sv;
+    }
+  __syncthreads();
+  if (tid < QR * RR) {
+    const int r = tid / RR, k = tid % RR;
+    double sv = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) sv += red[w][tid];
+    if (mb + r < M && k < R) mu[(mb + r) * R + k] = sv;
+  }
+}
+
 // mu[m, r] = sum_i k(xs_m, x_i) alpha[i, r]: one thread per query, training points and alpha staged
 // through shared memory in chunks; K* is never stored.
 template <int D, int RR>
@@ -167,6 +240,31 @@ int launch_cross_cov_t(const double* X, long long N, int D, const Theta& th, con
   else cross_cov_t_kernel<3><<<gridDim, 256, 0, stream>>>(X, N, th, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad);
   GPM_LAUNCH_CHECK();
   return 0;
+}
+
+template <int D>
+static int launch_ccm_d(const double* X, long long N, const Theta& th, const double* alpha, int R, const double* Xs,
+                        const gpm_grid_t& g, int use_grid, long long m0, long long M, double* KsT, long long ldks,
+                        long long ncols_pad, double* mu, cudaStream_t stream) {
+  const unsigned blocks = (unsigned)((M + 7) / 8);
+  if (R <= 1) cross_cov_mean_kernel<D, 1><<<blocks, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad, mu);
+  else if (R <= 2) cross_cov_mean_kernel<D, 2><<<blocks, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad, mu);
+  else return -1;
+  GPM_LAUNCH_CHECK();
+  return 0;
+}
+
+// fused cross-covariance + mean; returns -1 when R is too large for the fused kernel (caller falls back to
+// the separate mean kernel + plain cross-covariance)
+int launch_cross_cov_mean(const double* X, long long N, int D, const Theta& th, const double* alpha, int R,
+                          const double* Xs, const gpm_grid_t* grid, long long m0, long long M, double* KsT,
+                          long long ldks, long long ncols_pad, double* mu, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  gpm_grid_t g = {};
+  if (grid) g = *grid;
+  const int use_grid = Xs == nullptr;
+  return D == 2 ? launch_ccm_d<2>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad, mu, stream)
+                : launch_ccm_d<3>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad, mu, stream);
 }
 
 template <int D>

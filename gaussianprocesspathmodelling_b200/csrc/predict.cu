@@ -16,6 +16,9 @@ namespace gpm {
 int launch_cross_cov_t(const double* X, long long N, int D, const Theta& th, const double* Xs,
                        const gpm_grid_t* grid, long long m0, long long M, double* KsT, long long ldks,
                        long long ncols_pad, cudaStream_t stream);
+int launch_cross_cov_mean(const double* X, long long N, int D, const Theta& th, const double* alpha, int R,
+                          const double* Xs, const gpm_grid_t* grid, long long m0, long long M, double* KsT,
+                          long long ldks, long long ncols_pad, double* mu, cudaStream_t stream);
 int launch_predict_mean(const double* X, long long N, int D, const Theta& th, const double* alpha, int R,
                         const double* Xs, const gpm_grid_t* grid, long long m0, long long M, double* mu,
                         cudaStream_t stream);
@@ -70,11 +73,14 @@ extern "C" int gpm_predict(gpm_handle_t handle, const double* X, int64_t N, int3
   const long long M = m1 - m0;
   if (M == 0) return 0;
   int rc;
+  bool fuse_mean = false;
   if (flags & GPM_PREDICT_MEAN) {
     GPM_ARG(alpha != nullptr, 9);
     GPM_ARG(R >= 1 && R <= 8, 10);
     GPM_ARG(mu != nullptr, 15);
-    if ((rc = launch_predict_mean(X, N, D, th, alpha, R, Xs, grid, m0, M, mu, st))) return rc;
+    // with the variance requested and R <= 2 the mean is fused into the cross-covariance pass below
+    fuse_mean = (flags & GPM_PREDICT_VAR) && R <= 2 && getenv("GPM_NO_FUSED_MEAN") == nullptr;
+    if (!fuse_mean && (rc = launch_predict_mean(X, N, D, th, alpha, R, Xs, grid, m0, M, mu, st))) return rc;
   }
   if (!(flags & GPM_PREDICT_VAR)) return 0;
   GPM_ARG(L != nullptr && ((uintptr_t)L & 15) == 0, 6);
@@ -98,7 +104,11 @@ extern "C" int gpm_predict(gpm_handle_t handle, const double* X, int64_t N, int3
     const long long mc = (M - c0) < rows ? (M - c0) : rows;
     const int tiles = (int)((mc + NB - 1) / NB);
     GPM_CUDA(cudaMemsetAsync(rowsq, 0, (size_t)mc * sizeof(double), st));
-    if ((rc = launch_cross_cov_t(X, N, D, th, Xs, grid, m0 + c0, mc, W, npad, npad, st))) return rc;
+    if (fuse_mean)
+      rc = launch_cross_cov_mean(X, N, D, th, alpha, R, Xs, grid, m0 + c0, mc, W, npad, npad, mu + c0 * R, st);
+    else
+      rc = launch_cross_cov_t(X, N, D, th, Xs, grid, m0 + c0, mc, W, npad, npad, st);
+    if (rc) return rc;
     const bool per_step = getenv("GPM_VAR_STEPS") != nullptr;        // debugging: one launch per block column
     GemmArgs a = {};
     a.C = W; a.ldc = npad;
