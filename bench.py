@@ -358,7 +358,8 @@ def run_b200(args):
     roofline = {
         "kernel": "gemm_nt_kernel (DMMA.8x8x4 + TMA): the fused blocked-TRSM sweep of the posterior variance, one persistent launch",
         "bound": "tensor", "achieved": var_tflops, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s",
-        "frac": var_tflops / peaks["fp64_tflops"], "traffic": ncu_traffic(),
+        "frac": var_tflops / peaks["fp64_tflops"],
+        "traffic": (ncu_traffic() or {}).get("bytes_per_launch"), "traffic_detail": ncu_traffic(),
         "peak_source": peaks["fp64_src"],
         "launches_per_step": int(gemm_launches), "flops_per_launch": var_flops / max(1, gemm_launches),
         "avg_launch_ms": phases["predict_var_ms"] / max(1, gemm_launches),
