@@ -105,6 +105,20 @@ class GPModel:
             raise np.linalg.LinAlgError(f"covariance matrix is not positive definite: pivot {j} <= 0")
         return self
 
+    # -- checkpoint / resume (the model handle is just device tensors) -------------
+    def state_dict(self):
+        """Everything needed to predict again, as CPU tensors / arrays (``torch.save``-able)."""
+        return {"X": self.X.cpu(), "theta": np.asarray(self.theta), "K": self.K.cpu(), "ws": self.ws.cpu(),
+                "alpha": self.alpha.cpu(), "lml": self.lml_dev.cpu(), "info": self.info.cpu(), "version": 1}
+
+    @classmethod
+    def from_state_dict(cls, state, device=None):
+        torch = _torch()
+        dev = device or "cuda"
+        t = lambda a: a.to(dev) if isinstance(a, torch.Tensor) else torch.as_tensor(a).to(dev)   # noqa: E731
+        return cls(t(state["X"]).contiguous(), np.asarray(state["theta"], dtype=np.float64), t(state["K"]).contiguous(),
+                   t(state["ws"]).contiguous(), t(state["alpha"]).contiguous(), t(state["lml"]), t(state["info"]))
+
     def lml_grad(self):
         """d lml_r / d log(theta_j) as a numpy (R, D+2) array, j over [l_1..l_D, signal_var, noise_var]
         (R&W eq. 5.9; K^{-1} is formed on the tensor cores)."""

@@ -446,3 +446,14 @@ def test_many_query_points_small_model():
     assert nrm(mu.view(-1, 1)[idx].cpu().numpy(), mu_o) < MEAN_TOL
     assert nrm(var.view(-1)[idx].cpu().numpy(), var_o) < VAR_TOL
     assert bool(torch.isfinite(var).all())
+
+
+def test_model_checkpoint_roundtrip(tmp_path):
+    X, Y, th = wl.single_path(300, seed=4, D=3, R=2)
+    m = GPmap.fit_gp(X, Y, theta=th)
+    mu, var = m.predict_grid(wl.BOX, (21, 17), t=5.0)
+    f = tmp_path / "model.pt"
+    torch.save(m.state_dict(), f)
+    m2 = GPmap.GPModel.from_state_dict(torch.load(f, weights_only=False))
+    mu2, var2 = m2.predict_grid(wl.BOX, (21, 17), t=5.0)
+    assert torch.equal(mu, mu2) and torch.equal(var, var2) and np.array_equal(m.lml, m2.lml)
