@@ -255,15 +255,21 @@ def fit_gp_batched(Xb, Yb, lengthscale=None, signal_var=1.0, noise_var=1e-2, the
     R = Yb.shape[2]
     if theta is None:
         theta = make_theta(lengthscale, signal_var, noise_var, D)
-    theta = np.asarray(theta, dtype=np.float64)
+    theta = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))     # (D+2,) shared or (B, D+2) per path
+    if theta.shape not in ((D + 2,), (B, D + 2)):
+        raise ValueError(f"theta must have shape ({D + 2},) or ({B}, {D + 2})")
+    stride = D + 2 if theta.ndim == 2 else 0
     h = _native.handle(Xb.device.index or 0)
     alpha = torch.empty((B, N, R), dtype=torch.float64, device=Xb.device)
     lml = torch.empty((B, R), dtype=torch.float64, device=Xb.device)
     info = torch.zeros(B, dtype=torch.int32, device=Xb.device)
     ws = torch.empty(int(lib.gpm_fit_batched_workspace_bytes(B, N)) // 8, dtype=torch.float64, device=Xb.device)
-    rc = lib.gpm_fit_batched(h, _ptr(Xb), _ptr(Yb), B, N, D, R, _native.theta_array(theta), 0,
+    th_arr = _native.theta_array(theta.ravel())
+    rc = lib.gpm_fit_batched(h, _ptr(Xb), _ptr(Yb), B, N, D, R, th_arr, stride,
                              _ptr(alpha), _ptr(lml), _ptr(info), _ptr(ws), _stream(Xb))
     _native.check(rc, "gpm_fit_batched")
+    if stride:
+        torch.cuda.current_stream(Xb.device).synchronize()      # the host theta array is read by an async copy
     if check:
         bad = torch.nonzero(info)
         if bad.numel():

@@ -6,7 +6,8 @@
 namespace gpm {
 
 int launch_cov(const double* X, long long N, int D, const Theta& th, double* K, long long ldk,
-               int lower_only, int batch, long long batch_x, long long batch_k, cudaStream_t stream);
+               int lower_only, int batch, long long batch_x, long long batch_k, cudaStream_t stream,
+               const double* theta_dev, int theta_stride);
 int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, double* invD, int* info,
                   int batch, long long batch_rows, cudaStream_t s0);
 int solve_blocked(const double* L, long long N, long long ldl, const double* invD, double* alpha, int R,
@@ -26,7 +27,7 @@ using namespace gpm;
 extern "C" size_t gpm_fit_batched_workspace_bytes(int64_t B, int64_t N) {
   if (B <= 0 || N <= 0) return 0;
   const long long np = round_up_ll(N, NB);
-  return (size_t)B * (size_t)(np * np + np * NB) * sizeof(double);
+  return (size_t)B * (size_t)(np * np + np * NB + 8) * sizeof(double);   // + per-path theta
 }
 
 extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const double* Yb, int64_t B, int64_t N,
@@ -38,9 +39,10 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
   GPM_ARG(B > 0 && B <= 65535, 4);
   GPM_ARG(N > 0 && B * ((N + NB - 1) / NB * NB) < (1ll << 31), 5);
   Theta th;
-  GPM_ARG(make_theta(theta, D, &th) == 0, 8);
   GPM_ARG(R >= 1 && R <= 8, 7);
-  GPM_ARG(theta_stride == 0, 9);       /* per-path theta: not implemented in this round */
+  GPM_ARG(theta_stride == 0 || theta_stride == D + 2, 9);
+  GPM_ARG(theta != nullptr && (D == 2 || D == 3), 8);
+  for (int64_t b = 0; b < (theta_stride ? B : 1); b++) GPM_ARG(make_theta(theta + b * theta_stride, D, &th) == 0, 8);
   GPM_ARG(alpha != nullptr && alpha != Yb, 10);
   GPM_ARG(info != nullptr, 12);
   GPM_ARG(ws != nullptr && ((uintptr_t)ws & 15) == 0, 13);
@@ -51,7 +53,13 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
   double* Kb = reinterpret_cast<double*>(ws);            // B stacked np x np matrices, ld = np
   double* invD = Kb + (long long)B * np * np;            // B x nblk x NB x NB
   int rc;
-  if ((rc = launch_cov(Xb, N, D, th, Kb, np, 1, (int)B, N * D, np * np, st))) return rc;
+  const double* theta_dev = nullptr;
+  if (theta_stride) {                                      // per-path theta: staged after the inverse blocks
+    double* tdev = invD + (long long)B * nblk * NB * NB;
+    GPM_CUDA(cudaMemcpyAsync(tdev, theta, (size_t)B * (D + 2) * sizeof(double), cudaMemcpyHostToDevice, st));
+    theta_dev = tdev;
+  }
+  if ((rc = launch_cov(Xb, N, D, th, Kb, np, 1, (int)B, N * D, np * np, st, theta_dev, (int)theta_stride))) return rc;
   if ((rc = potrf_blocked(h, Kb, N, np, invD, info, (int)B, np, st))) return rc;
   rc = solve_paths(Kb, N, np, invD, Yb, alpha, lml, R, (int)B, np * np, (long long)nblk * NB * NB, N * R, st);
   if (rc >= 0) return rc;

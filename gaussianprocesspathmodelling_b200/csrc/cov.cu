@@ -12,9 +12,17 @@ constexpr int CT_LD = CT + 1;     // padded smem pitch
 template <int D>
 __global__ void __launch_bounds__(256)
 cov_kernel(const double* __restrict__ X, long long N, Theta th, double* __restrict__ K,
-           long long ldk, int lower_only, long long batch_x, long long batch_k) {
+           long long ldk, int lower_only, long long batch_x, long long batch_k,
+           const double* __restrict__ theta_dev, int theta_stride) {
   __shared__ double xi[CT][3], xj[CT][3];
   __shared__ double tile[CT][CT_LD];
+  if (theta_dev) {                                  // per-path hyper-parameters: [l_1..l_D, sf2, sn2] per batch index
+    const double* t = theta_dev + (long long)blockIdx.y * theta_stride;
+#pragma unroll
+    for (int d = 0; d < D; d++) th.l[d] = t[d];
+    th.sf2 = t[D];
+    th.sn2 = t[D + 1];
+  }
   // lower-triangular tile enumeration
   const int b = blockIdx.x;
   int ti = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
@@ -219,11 +227,12 @@ predict_mean_kernel(const double* __restrict__ X, long long N, Theta th, const d
 }
 
 int launch_cov(const double* X, long long N, int D, const Theta& th, double* K, long long ldk,
-               int lower_only, int batch, long long batch_x, long long batch_k, cudaStream_t stream) {
+               int lower_only, int batch, long long batch_x, long long batch_k, cudaStream_t stream,
+               const double* theta_dev, int theta_stride) {
   const int T = (int)((N + CT - 1) / CT);
   dim3 grid(T * (T + 1) / 2, batch);
-  if (D == 2) cov_kernel<2><<<grid, 256, 0, stream>>>(X, N, th, K, ldk, lower_only, batch_x, batch_k);
-  else cov_kernel<3><<<grid, 256, 0, stream>>>(X, N, th, K, ldk, lower_only, batch_x, batch_k);
+  if (D == 2) cov_kernel<2><<<grid, 256, 0, stream>>>(X, N, th, K, ldk, lower_only, batch_x, batch_k, theta_dev, theta_stride);
+  else cov_kernel<3><<<grid, 256, 0, stream>>>(X, N, th, K, ldk, lower_only, batch_x, batch_k, theta_dev, theta_stride);
   GPM_LAUNCH_CHECK();
   return 0;
 }
@@ -304,7 +313,7 @@ extern "C" int gpm_cov(gpm_handle_t h, const double* X, int64_t N, int32_t D, co
   GPM_ARG(make_theta(theta, D, &th) == 0, 5);
   GPM_ARG(K != nullptr && ((uintptr_t)K & 15) == 0, 6);
   GPM_ARG(ldk >= N && (ldk & 1) == 0, 7);
-  return launch_cov(X, N, D, th, K, ldk, (flags & GPM_COV_LOWER) ? 1 : 0, 1, 0, 0, (cudaStream_t)stream);
+  return launch_cov(X, N, D, th, K, ldk, (flags & GPM_COV_LOWER) ? 1 : 0, 1, 0, 0, (cudaStream_t)stream, nullptr, 0);
 }
 
 extern "C" int gpm_cross_cov(gpm_handle_t h, const double* X, int64_t N, int32_t D, const double* theta,

@@ -457,3 +457,14 @@ def test_model_checkpoint_roundtrip(tmp_path):
     m2 = GPmap.GPModel.from_state_dict(torch.load(f, weights_only=False))
     mu2, var2 = m2.predict_grid(wl.BOX, (21, 17), t=5.0)
     assert torch.equal(mu, mu2) and torch.equal(var, var2) and np.array_equal(m.lml, m2.lml)
+
+
+def test_batched_per_path_hyperparameters():
+    Xb, Yb, th = wl.batched_paths(5, 200, seed=3, D=3, R=2)
+    rng = np.random.default_rng(2)
+    ths = np.stack([th * np.array([rng.uniform(0.5, 2), rng.uniform(0.5, 2), rng.uniform(0.5, 2), rng.uniform(0.5, 2), rng.uniform(0.3, 3)])
+                    for _ in range(5)])
+    alpha, lml = GPmap.fit_gp_batched(Xb, Yb, theta=ths)
+    a_o, l_o = gp_ref.fit_batched(Xb, Yb, ths)
+    assert nrm(alpha.cpu().numpy(), a_o) < MEAN_TOL
+    assert np.abs(lml.cpu().numpy() - l_o).max() < LML_TOL * np.abs(l_o).max()
