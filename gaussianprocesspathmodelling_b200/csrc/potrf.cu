@@ -388,7 +388,9 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
     }
     a.a_row0 = jlo * NB; a.b_row0 = jlo * NB;
     a.c_row0 = (long long)jlo * NB; a.c_col0 = (long long)jlo * NB;
-    a.max_tiles_per_cta = lookahead ? (kw > 1 ? 4 : 8) : 16;   // keep CTAs short enough for the panel stream
+    static const int tpc_wide = getenv("GPM_TPC_WIDE") ? atoi(getenv("GPM_TPC_WIDE")) : 4;
+    static const int tpc_narrow = getenv("GPM_TPC_NARROW") ? atoi(getenv("GPM_TPC_NARROW")) : 8;
+    a.max_tiles_per_cta = lookahead ? (kw > 1 ? tpc_wide : tpc_narrow) : 16;   // keep CTAs short enough for the panel stream
     return launch_gemm(h, mapK, mapK, mapK, a, batch, st);
   };
   // factor the block columns of one outer panel [b0, b0+w): potf2 + panel solve per 128-column block,
@@ -407,7 +409,8 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
   // prologue/epilogue of K = 128) while the trailing matrix is large enough to hide the longer panel
   // chain behind the rest-update, width 1 for the tail.  Large batches are throughput-bound in every
   // launch, so they always use width 2 and no look-ahead.
-  const int wide_min = (batch >= 32) ? 2 : 48;       // remaining block columns needed for a width-2 panel
+  static const int wide_env = getenv("GPM_WIDE_MIN") ? atoi(getenv("GPM_WIDE_MIN")) : 48;
+  const int wide_min = (batch >= 32) ? 2 : wide_env; // remaining block columns needed for a width-2 panel
   std::vector<int> pb(nblk + 1), pw(nblk + 1);
   int npanel = 0;
   for (int b = 0; b < nblk;) {

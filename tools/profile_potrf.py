@@ -3,12 +3,12 @@ import argparse, ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 from gaussianprocesspathmodelling_b200 import _native, workloads as wl  # noqa: E402
-ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=16384); ap.add_argument("--reps", type=int, default=2)
+ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=16384); ap.add_argument("--reps", type=int, default=2); ap.add_argument("--pad", type=int, default=0)
 a = ap.parse_args()
 N = a.n
 X, Y, th = wl.single_path(N, 4, 2, 1)
 lib = _native.load(); h = _native.handle(0)
-Xd = torch.from_numpy(X).cuda(); ld = (N + 15) // 16 * 16
+Xd = torch.from_numpy(X).cuda(); ld = (N + 15) // 16 * 16 + a.pad
 K = torch.empty((N, ld), dtype=torch.float64, device="cuda")
 ws = torch.empty(int(lib.gpm_potrf_workspace_bytes(N)) // 8, dtype=torch.float64, device="cuda")
 info = torch.zeros(1, dtype=torch.int32, device="cuda")
