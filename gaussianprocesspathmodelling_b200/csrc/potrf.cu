@@ -11,6 +11,7 @@
 // bulk of step k's tensor-core work.
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "gemm.cuh"
@@ -390,31 +391,38 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
     a.c_row0 = (long long)jlo * NB; a.c_col0 = (long long)jlo * NB;
     static const int tpc_wide = getenv("GPM_TPC_WIDE") ? atoi(getenv("GPM_TPC_WIDE")) : 4;
     static const int tpc_narrow = getenv("GPM_TPC_NARROW") ? atoi(getenv("GPM_TPC_NARROW")) : 8;
-    a.max_tiles_per_cta = lookahead ? (kw > 1 ? tpc_wide : tpc_narrow) : 16;   // keep CTAs short enough for the panel stream
+    a.max_tiles_per_cta = lookahead ? (kw > 2 ? 2 : (kw > 1 ? tpc_wide : tpc_narrow)) : 16;   // keep CTAs short enough for the panel stream
     return launch_gemm(h, mapK, mapK, mapK, a, batch, st);
   };
-  // factor the block columns of one outer panel [b0, b0+w): potf2 + panel solve per 128-column block,
-  // with the in-panel update of the second block column (K = 128)
+  // factor the block columns of one outer panel [b0, b0+w): potf2 + panel solve per 128-column block;
+  // inside the panel each block column is first updated with the panel's earlier blocks (left-looking)
   auto outer_panel = [&](int b0, int w, cudaStream_t st) -> int {
     int r;
-    if ((r = panel(b0, st))) return r;
-    if (w > 1) {
-      if ((r = update(b0, 1, b0 + 1, b0 + 2, st))) return r;
-      if ((r = panel(b0 + 1, st))) return r;
+    for (int j = 0; j < w; j++) {
+      if (j > 0 && (r = update(b0, j, b0 + j, b0 + j + 1, st))) return r;
+      if ((r = panel(b0 + j, st))) return r;
     }
     return 0;
   };
 
-  // Outer panels: width 2 (K = 256 trailing updates: half the C traffic and half the per-tile
-  // prologue/epilogue of K = 128) while the trailing matrix is large enough to hide the longer panel
-  // chain behind the rest-update, width 1 for the tail.  Large batches are throughput-bound in every
-  // launch, so they always use width 2 and no look-ahead.
+  // Outer panels: wide panels make the trailing updates deep (K = 256 or 512: less C traffic and the tile
+  // prologue/epilogue amortised over more slabs) but lengthen the serial panel chain, which must stay
+  // hidden behind the rest-update: width 8 while >= 96 block columns remain, 4 while >= 64, 2 while >= 48,
+  // then 1 (thresholds swept on B200 at N = 8192 and 16384, tools/potrf_sweep.sh).
+  // Large batches are throughput-bound in every launch, so they use width 2 and no look-ahead.
   static const int wide_env = getenv("GPM_WIDE_MIN") ? atoi(getenv("GPM_WIDE_MIN")) : 48;
-  const int wide_min = (batch >= 32) ? 2 : wide_env; // remaining block columns needed for a width-2 panel
+  static const int wide4_env = getenv("GPM_WIDE4_MIN") ? atoi(getenv("GPM_WIDE4_MIN")) : 64;
+  static const int wide8_env = getenv("GPM_WIDE8_MIN") ? atoi(getenv("GPM_WIDE8_MIN")) : 96;
   std::vector<int> pb(nblk + 1), pw(nblk + 1);
   int npanel = 0;
   for (int b = 0; b < nblk;) {
-    const int w = (nblk - b >= wide_min && b + 1 < nblk) ? 2 : 1;
+    const int left = nblk - b;
+    int w = 1;
+    if (batch >= 32) w = left >= 2 ? 2 : 1;
+    else if (left >= wide8_env) w = 8;
+    else if (left >= wide4_env) w = 4;
+    else if (left >= wide_env) w = 2;
+    w = std::min(w, left);
     pb[npanel] = b; pw[npanel] = w; npanel++;
     b += w;
   }
