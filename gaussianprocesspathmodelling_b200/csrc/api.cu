@@ -92,7 +92,6 @@ int gpm_create(gpm_handle_t* handle, int device) {
   h->ev = new cudaEvent_t[h->n_ev];
   for (int i = 0; i < h->n_ev; i++) GPM_CUDA(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
   h->n_flags = 8192;                  // up to N = 2^20
-  h->epoch = 0;
   GPM_CUDA(cudaMalloc(&h->flags, 2 * h->n_flags * sizeof(int)));
   GPM_CUDA(cudaMemset(h->flags, 0, 2 * h->n_flags * sizeof(int)));
   *handle = reinterpret_cast<gpm_handle_t>(h);

@@ -67,8 +67,7 @@ struct gpm_handle_impl {
   int n_ev;
   PFN_cuTensorMapEncodeTiled_v12000 encode;
   int* flags;                       // 2 x n_flags device ints: block-published flags of the chained solves
-  int n_flags;
-  int epoch;                        // flag value of the current solve (monotonic, so flags need no clearing)
+  int n_flags;                      //   (cleared on the stream at the start of every solve: graph-replay safe)
 };
 
 // 2-D row-major float64 tensor map with a [rows_box x 16] box and 128-byte swizzle.

@@ -168,8 +168,8 @@ lml_kernel(const double* __restrict__ L, long long ldl, long long N, const doubl
 // ------------------------------------------------------------------------------------------------
 // Single-matrix path: one cooperative launch per direction.  CTA c owns block rows c, c+G, ... and
 // sweeps the 128x128 tiles of its block row (forward) / block column (backward) as the solution
-// blocks it depends on are published by their owners (release/acquire flags in global memory; the
-// flag value is the call's epoch so the arrays never need clearing).  L is streamed from HBM once
+// blocks it depends on are published by their owners (release/acquire flags in global memory, cleared
+// on the stream before each solve so that a captured CUDA graph can be replayed).  L is streamed from HBM once
 // per direction with 128 KB in flight per CTA; the critical path is one flag hand-off per block.
 // ------------------------------------------------------------------------------------------------
 // acc[0..RR) += s * zrow[0..RR)  with 128-bit shared loads (zrow 16-byte aligned when RR is even)
