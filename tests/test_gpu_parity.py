@@ -468,3 +468,18 @@ def test_batched_per_path_hyperparameters():
     a_o, l_o = gp_ref.fit_batched(Xb, Yb, ths)
     assert nrm(alpha.cpu().numpy(), a_o) < MEAN_TOL
     assert np.abs(lml.cpu().numpy() - l_o).max() < LML_TOL * np.abs(l_o).max()
+
+
+def test_run_to_run_determinism():
+    # look-ahead streams, flag-chained solves and the multi-op sweep must not make results timing-dependent
+    X, Y, th = wl.single_path(1500, seed=7, D=2, R=2)
+    ref = None
+    for _ in range(6):
+        m = GPmap.fit_gp(X, Y, theta=th)
+        mu, var = m.predict_grid(wl.BOX, (120, 97))
+        cur = (m.alpha.clone(), m.lml_dev.clone(), mu.clone(), var.clone(), m.lml_grad())
+        if ref is None:
+            ref = cur
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(ref[:4], cur[:4]))
+            assert np.array_equal(ref[4], cur[4])
