@@ -39,6 +39,9 @@ struct OpDesc {
   int nslab, a_col0, b_col0, b_row, epi;
   long long c_col;
   bool second_b, rowsq;
+  bool a_smem;     // sweep: the A operand is the previous op's result, resident in the C-tile buffer
+  bool to_smem;    // sweep: the result stays in the C-tile buffer (swizzled slab layout) instead of going to global
+  bool signal;     // sweep: publish the global stores of this op (the next update reads them by TMA)
 };
 
 __device__ __forceinline__ OpDesc make_op(const GemmArgs& p, const TileCoord& tc, int o, long long bz) {
@@ -55,6 +58,9 @@ __device__ __forceinline__ OpDesc make_op(const GemmArgs& p, const TileCoord& tc
     d.c_col = (long long)k * NB;
     d.second_b = !isU;
     d.rowsq = !isU;
+    d.a_smem = !isU && o > 0;     // D(k), k > k0: A = R left in shared memory by U(k); the first D reads K*^T from global
+    d.to_smem = isU;
+    d.signal = !isU;
   } else {
     const int lo = p.kstart_mode == 1 ? tc.ti * NB : 0;
     int hi = p.klen;
@@ -69,6 +75,7 @@ __device__ __forceinline__ OpDesc make_op(const GemmArgs& p, const TileCoord& tc
     d.c_col = p.c_col0 + (long long)tc.tj * NB + bz * p.batch_cols;
     d.second_b = false;
     d.rowsq = p.rowsq != nullptr;
+    d.a_smem = d.to_smem = d.signal = false;
   }
   return d;
 }
@@ -120,27 +127,35 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       prefetch_tmap(&mapB);
       prefetch_tmap(&mapC);
       if (chained) prefetch_tmap(&mapB2);
-      int sg = 0, ct = 0, nop = 0;
+      int sg = 0, ct = 0, nsig = 0;        // ring slot counter, C prefetches issued, signalling ops issued
       for (int t = t_begin; t < t_end; t++) {
         const TileCoord tc = tile_coord(p, tile_id(t));
         const int a_row = p.a_row0 + tc.ti * NB + (int)(bz * p.batch_a_rows);
         const int nops = ops_of(tc);
-        for (int o = 0; o < nops; o++, nop++) {
+        for (int o = 0; o < nops; o++) {
           const OpDesc d = make_op(p, tc, o, bz);
           const bool sub = d.epi == EPI_SUB;
-          // chained ops read what the previous op of this CTA stored: wait until it is visible
-          if (chained && nop > 0) mbar_wait(bar_dep, (nop - 1) & 1);
           const int c_at = min(STAGES - 1, d.nslab - 1);      // issue the C prefetch after this slab
+          // sweep: an update reads the block column the previous diagonal multiply stored (its last 8 slabs)
+          const int dep_at = (chained && sub && nsig > 0) ? max(0, d.nslab - NB / SLAB_K) : -1;
           for (int s = 0; s < d.nslab; s++, sg++) {
+            if (s == dep_at) mbar_wait(bar_dep, (nsig - 1) & 1);
             const int st = sg % STAGES;
             if (sg >= STAGES) mbar_wait(bar_empty + st * 8, ((sg / STAGES) - 1) & 1);
-            mbar_arrive_expect_tx(bar_full + st * 8, 2 * SLAB_BYTES);
             const uint32_t dst = base + st * 2 * SLAB_BYTES;
-            tma_load_2d(dst, &mapA, d.a_col0 + s * SLAB_K, a_row, bar_full + st * 8);
+            if (d.a_smem) {
+              mbar_arrive_expect_tx(bar_full + st * 8, SLAB_BYTES);
+            } else {
+              mbar_arrive_expect_tx(bar_full + st * 8, 2 * SLAB_BYTES);
+              tma_load_2d(dst, &mapA, d.a_col0 + s * SLAB_K, a_row, bar_full + st * 8);
+            }
             tma_load_2d(dst + SLAB_BYTES, d.second_b ? &mapB2 : &mapB, d.b_col0 + s * SLAB_K, d.b_row,
                         bar_full + st * 8);
             if (sub && s == c_at) {
-              if (ct > 0) mbar_wait(bar_cempty, (ct - 1) & 1);
+              // the C-tile buffer must be free: in the sweep it is busy until the previous diagonal multiply has
+              // finished (operand + row-sum scratch); otherwise until the previous epilogue has read it
+              if (chained) { if (nsig > 0) mbar_wait(bar_dep, (nsig - 1) & 1); }
+              else if (ct > 0) mbar_wait(bar_cempty, (ct - 1) & 1);
               mbar_arrive_expect_tx(bar_cfull, C_BYTES);
               const int c_row = (int)(p.c_row0 + (long long)tc.ti * NB + bz * p.batch_c_rows);
 #pragma unroll
@@ -149,6 +164,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               ct++;
             }
           }
+          if (d.signal) nsig++;
         }
       }
     }
@@ -180,7 +196,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int s = 0; s < d.nslab; s++, sg++) {
         const int st = sg % STAGES;
         mbar_wait(bar_full + st * 8, (sg / STAGES) & 1);
-        const uint32_t sa = base + st * 2 * SLAB_BYTES + a_warp;
+        const uint32_t sa = (d.a_smem ? cbuf + s * SLAB_BYTES : base + st * 2 * SLAB_BYTES) + a_warp;
         const uint32_t sb = base + st * 2 * SLAB_BYTES + b_warp;
 #pragma unroll
         for (int k4 = 0; k4 < 4; k4++) {
@@ -215,11 +231,18 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c0), "=d"(c1) : "r"(addr));
             acc[mt][nt][0] = c0 - acc[mt][nt][0];
             acc[mt][nt][1] = c1 - acc[mt][nt][1];
+            if (d.to_smem)        // same layout as an A-operand slab: the next op contracts over these columns
+              asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(acc[mt][nt][0]), "d"(acc[mt][nt][1]) : "memory");
           }
+        }
+        ct++;
+        if (d.to_smem) {
+          // the result stays on chip; every consumer warp must have written its part before anyone reads it
+          asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
+          continue;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_cempty);
-        ct++;
       }
       if (d.epi == EPI_NEG) {
 #pragma unroll
@@ -263,8 +286,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
       }
-      if (chained) {
-        // publish this op's global stores to the async proxy (TMA) before the producer loads them
+      if (d.signal) {
+        // publish this op's global stores to the async proxy (TMA) before the producer loads them; this also
+        // tells the producer that the C-tile buffer (operand + row-sum scratch of this op) is free again
         fence_proxy_async();
         __threadfence_block();
         __syncwarp();
