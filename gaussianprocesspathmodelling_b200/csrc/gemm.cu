@@ -13,7 +13,7 @@ namespace gpm {
 
 constexpr int STAGES = 3;
 constexpr int CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int GEMM_THREADS = (CONSUMER_WARPS + 4) * 32;   // two consumer warpgroups + one producer warpgroup (setmaxnreg)
 constexpr int C_BYTES = NB * NB * 8;
 constexpr int GEMM_SMEM = STAGES * 2 * SLAB_BYTES + C_BYTES + 1024 /*align slack*/ + (2 * STAGES + 3) * 8;
 
@@ -42,6 +42,7 @@ struct OpDesc {
   bool a_smem;     // sweep: the A operand is the previous op's result, resident in the C-tile buffer
   bool to_smem;    // sweep: the result stays in the C-tile buffer (swizzled slab layout) instead of going to global
   bool signal;     // sweep: publish the global stores of this op (the next update reads them by TMA)
+  bool tri_b;      // B is a lower-triangular 128x128 block: slab s is all zero for columns below 16 s
 };
 
 __device__ __forceinline__ OpDesc make_op(const GemmArgs& p, const TileCoord& tc, int o, long long bz) {
@@ -61,6 +62,7 @@ __device__ __forceinline__ OpDesc make_op(const GemmArgs& p, const TileCoord& tc
     d.a_smem = !isU && o > 0;     // D(k), k > k0: A = R left in shared memory by U(k); the first D reads K*^T from global
     d.to_smem = isU;
     d.signal = !isU;
+    d.tri_b = !isU;               // inv(L_kk)
   } else {
     const int lo = p.kstart_mode == 1 ? tc.ti * NB : 0;
     int hi = p.klen;
@@ -76,6 +78,7 @@ __device__ __forceinline__ OpDesc make_op(const GemmArgs& p, const TileCoord& tc
     d.second_b = false;
     d.rowsq = p.rowsq != nullptr;
     d.a_smem = d.to_smem = d.signal = false;
+    d.tri_b = p.tri_b != 0;
   }
   return d;
 }
@@ -120,8 +123,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   __syncthreads();
 
-  if (warp == CONSUMER_WARPS) {
-    // ===== TMA producer: one elected lane =====
+  if (warp >= CONSUMER_WARPS) {
+    // ===== producer warpgroup: hand its registers to the consumers; one elected lane of its first warp drives TMA =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp != CONSUMER_WARPS) return;
     if (lane == 0) {
       prefetch_tmap(&mapA);
       prefetch_tmap(&mapB);
@@ -172,7 +177,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 
   // ===== consumers: 2 (m) x 4 (n) warps, warp tile 64 x 32 =====
-  const int wm = warp >> 2, wn = warp & 3;
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  // The second row of warps takes the column groups in reverse order, so that each scheduler (warp % 4) holds
+  // column groups {w, 3-w}: when slabs are skipped for a triangular B (group w needs 2w+2 of 8 slabs), every
+  // scheduler keeps 10 of 16 slab-units and the saving is not lost to imbalance.
+  const int wm = warp >> 2, wn = (warp & 3) ^ (wm ? 3 : 0);
   const int g = lane >> 2, q = lane & 3;
   uint32_t off[4];
 #pragma unroll
@@ -198,6 +207,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(bar_full + st * 8, (sg / STAGES) & 1);
         const uint32_t sa = (d.a_smem ? cbuf + s * SLAB_BYTES : base + st * 2 * SLAB_BYTES) + a_warp;
         const uint32_t sb = base + st * 2 * SLAB_BYTES + b_warp;
+        if (!d.tri_b || s <= 2 * wn + 1) {
 #pragma unroll
         for (int k4 = 0; k4 < 4; k4++) {
           double a[8], b[4];
@@ -209,6 +219,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int mt = 0; mt < 8; mt++)
 #pragma unroll
             for (int nt = 0; nt < 4; nt++) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + st * 8);

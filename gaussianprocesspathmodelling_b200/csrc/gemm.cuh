@@ -32,6 +32,8 @@ struct GemmArgs {
   int sweep_nblk;
   int sweep_tri;          // sweep mode on a block-upper-triangular right-hand side (row block t is zero left of
                           // block column t): row block t starts at op D(t) and contracts from column t*NB
+  int tri_b;              // tile mode: the B block is lower triangular (an inverted diagonal block, B[n][c] = 0 for
+                          // c > n): a consumer warp skips the slabs that are all zero for its 32 columns
   // tile mode: triangular operands let a tile skip the structurally-zero part of the contraction
   int kstart_mode;        // 1: start at ti*NB (A zero left of its diagonal block)
   int kend_mode;          // 1: stop at (ti+1)*NB (A zero right of its diagonal block); 2: stop at (tj+1)*NB (same for B)

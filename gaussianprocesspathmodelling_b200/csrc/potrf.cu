@@ -369,6 +369,7 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
     a.c_row0 = (long long)(k + 1) * NB; a.c_col0 = (long long)k * NB;
     a.c_rows_end = N; a.c_cols_end = (long long)(k + 1) * NB;
     a.epi = EPI_STORE;
+    a.tri_b = 1;                                   // inv(L_kk) is lower triangular
     a.batch_a_rows = batch_rows; a.batch_b_rows = (long long)nblk * NB; a.batch_c_rows = batch_rows;
     return launch_gemm(h, mapK, mapInv, mapK, a, batch, st);
   };

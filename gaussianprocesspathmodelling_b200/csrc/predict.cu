@@ -125,10 +125,10 @@ extern "C" int gpm_predict(gpm_handle_t handle, const double* X, int64_t N, int3
         a.c_col0 = (long long)k * NB;
         a.c_cols_end = (long long)(k + 1) * NB;
         if (k > 0) {                       // W[:,k] -= W[:,0:k] L[k,0:k]^T
-          a.a_col0 = 0; a.b_col0 = 0; a.klen = k * NB; a.epi = EPI_SUB; a.rowsq = nullptr;
+          a.a_col0 = 0; a.b_col0 = 0; a.klen = k * NB; a.epi = EPI_SUB; a.rowsq = nullptr; a.tri_b = 0;
           if ((rc = launch_gemm(h, mapW, mapL, mapW, a, 1, st))) return rc;
         }
-        a.a_col0 = k * NB; a.b_col0 = 0; a.klen = NB; a.epi = EPI_STORE; a.rowsq = rowsq;   // W[:,k] *= inv(L_kk)^T
+        a.a_col0 = k * NB; a.b_col0 = 0; a.klen = NB; a.epi = EPI_STORE; a.rowsq = rowsq; a.tri_b = 1;   // W[:,k] *= inv(L_kk)^T
         if ((rc = launch_gemm(h, mapW, mapInv, mapW, a, 1, st))) return rc;
       }
     }
