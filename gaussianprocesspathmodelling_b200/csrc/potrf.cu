@@ -18,10 +18,9 @@
 
 namespace gpm {
 
-constexpr int XLD = 12;       // pitch of the 8-column panel staging buffer (conflict-free DMMA fragment reads)
 constexpr int NT8 = NB / 8;                         // 16 tiles per block edge
 constexpr int PACKED = NT8 * (NT8 + 1) / 2 * 64;    // doubles in the packed lower triangle (136 tiles)
-constexpr int POTF2_SMEM = (PACKED + NB * XLD + 64 + NB) * 8;   // 83 KB: two CTAs per SM
+constexpr int POTF2_SMEM = (PACKED + 64 + NB) * 8;  // 69.5 KB + 1.5 KB: three CTAs per SM
 
 // The 128x128 diagonal block lives in shared memory as its lower triangle of 8x8 tiles (tile (ti,tj),
 // tj <= ti, at index ti(ti+1)/2 + tj, 64 contiguous doubles, row-major).  Inside a tile the column is
@@ -32,27 +31,98 @@ __device__ __forceinline__ int tile_base(int ti, int tj) { return (ti * (ti + 1)
 __device__ __forceinline__ int in_tile(int i, int c) { return (i & 7) * 8 + ((c & 7) ^ (((i >> 1) & 1) << 2)); }
 __device__ __forceinline__ int toff(int i, int c) { return tile_base(i >> 3, c >> 3) + in_tile(i, c); }
 
-// 8x8 lower Cholesky in one thread's registers (right-looking, so the serial chain per column is
+// 4x4 lower Cholesky in one thread's registers (right-looking, so the serial chain per column is
 // rsqrt -> scale -> one FMA).  a: packed lower (a[i*(i+1)/2 + j]); on exit a holds L and r[j] = 1/L_jj.
 // Every loop has constant bounds with compile-time-foldable guards so the arrays stay in registers.
 // Returns the 1-based index of the first non-positive pivot (0 if none).
-__device__ __forceinline__ int chol8(double (&a)[36], double (&r)[8]) {
+__device__ __forceinline__ int chol4(double (&a)[10], double (&r)[4]) {
   int bad = 0;
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
+  for (int j = 0; j < 4; j++) {
     double d = a[j * (j + 1) / 2 + j];
     if (!(d > 0.0) || !(d < 1.0e300)) { if (!bad) bad = j + 1; d = 1.0; }
     r[j] = rsqrt(d);                       // 1 ulp; sqrt + divide would cost ~5x the latency on this serial path
     a[j * (j + 1) / 2 + j] = d * r[j];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 4; i++)
       if (i > j) a[i * (i + 1) / 2 + j] *= r[j];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int c = 0; c < 8; c++)
+      for (int c = 0; c < 4; c++)
         if (i > j && c > j && c <= i)
           a[i * (i + 1) / 2 + c] = fma(-a[i * (i + 1) / 2 + j], a[c * (c + 1) / 2 + j], a[i * (i + 1) / 2 + c]);
+  }
+  return bad;
+}
+
+// 8x8 lower Cholesky of the diagonal tile at sm[tb0..] by ONE thread, as a 2x2 blocking of 4x4 blocks:
+// factor A11, solve L21, update and factor A22.  At most 26 matrix entries are live at a time (a flat 8x8
+// keeps 36 + 8 doubles live, which no longer fits the 85-register budget of three CTAs per SM); every
+// element still sees the same sequence of operations as the flat right-looking form.  Writes L into the
+// tile and into l8 (packed), 1/L_jj into rd8.  Returns the 1-based index of the first bad pivot or 0.
+__device__ __forceinline__ int chol8_tile(double* sm, int tb0, double* l8, double* rd8) {
+  double a[10], r[4], x[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (j <= i) a[i * (i + 1) / 2 + j] = sm[tb0 + in_tile(i, j)];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) x[i][c] = sm[tb0 + in_tile(4 + i, c)];
+  int bad = chol4(a, r);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    rd8[i] = r[i];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (j <= i) { sm[tb0 + in_tile(i, j)] = a[i * (i + 1) / 2 + j]; l8[i * (i + 1) / 2 + j] = a[i * (i + 1) / 2 + j]; }
+  }
+  // L21 = A21 * inv(L11)^T
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      double v = x[i][c];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (k < c) v = fma(-x[i][k], a[c * (c + 1) / 2 + k], v);
+      x[i][c] = v * r[c];
+    }
+  double b[10], r2[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (j <= i) b[i * (i + 1) / 2 + j] = sm[tb0 + in_tile(4 + i, 4 + j)];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      sm[tb0 + in_tile(4 + i, c)] = x[i][c];
+      l8[(4 + i) * (5 + i) / 2 + c] = x[i][c];
+    }
+  // A22 -= L21 L21^T
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (j <= i) b[i * (i + 1) / 2 + j] = fma(-x[i][k], x[j][k], b[i * (i + 1) / 2 + j]);
+  const int bad2 = chol4(b, r2);
+  if (!bad && bad2) bad = 4 + bad2;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    rd8[4 + i] = r2[i];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (j <= i) {
+        sm[tb0 + in_tile(4 + i, 4 + j)] = b[i * (i + 1) / 2 + j];
+        l8[(4 + i) * (5 + i) / 2 + 4 + j] = b[i * (i + 1) / 2 + j];
+      }
   }
   return bad;
 }
@@ -134,12 +204,11 @@ __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
 // DMMA tiles.  The kernel is latency-bound (serial pivot chain, barrier hand-offs), so it is sized
 // for two CTAs per SM (83 KB shared memory, 256 threads): batched fits keep both busy.
 template <int P2_THREADS>
-__global__ void __launch_bounds__(P2_THREADS, 512 / P2_THREADS)
+__global__ void __launch_bounds__(P2_THREADS, P2_THREADS == 256 ? 3 : 1)
 potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, double* __restrict__ invD,
                  int* __restrict__ info, long long batch_k, long long batch_inv) {
   extern __shared__ __align__(16) double sm[];
-  double* xp = sm + PACKED;            // [128][XLD] current panel
-  double* l8 = xp + NB * XLD;          // [36] current 8x8 factor (packed lower)
+  double* l8 = sm + PACKED;            // [36] current 8x8 factor (packed lower)
   double* rd = l8 + 64;                // [128] reciprocals of the diagonal of L
   constexpr int P2_WARPS = P2_THREADS / 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -168,27 +237,14 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
 
   const int g = lane >> 2, q = lane & 3;
   const int c_in = g * 8 + ((2 * q) ^ (((g >> 1) & 1) << 2));
+  const int x_in = g * 8 + (q ^ (((g >> 1) & 1) << 2));          // panel fragment: row g, column q
+  const int x4 = (x_in ^ 4) - x_in;                               // ... and column q + 4
   for (int p = 0; p < 16; p++) {
     const int c0 = 8 * p;
     // (1) 8x8 diagonal block: factor in one thread
     if (tid == 0) {
-      double a[36], r[8];
-      const int tb0 = tile_base(p, p);
-#pragma unroll
-      for (int i = 0; i < 8; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) a[i * (i + 1) / 2 + j] = sm[tb0 + in_tile(i, j)];
-      const int bad = chol8(a, r);
+      const int bad = chol8_tile(sm, tile_base(p, p), l8, rd + c0);
       if (bad && c0 + bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + c0 + bad));
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        rd[c0 + i] = r[i];
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-          sm[tb0 + in_tile(i, j)] = a[i * (i + 1) / 2 + j];
-          l8[i * (i + 1) / 2 + j] = a[i * (i + 1) / 2 + j];
-        }
-      }
     }
     __syncthreads();
     // (2) panel solve by forward substitution, one thread per row below the block:
@@ -206,13 +262,13 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
         x[c] = v * rd[c0 + c];
       }
 #pragma unroll
-      for (int c = 0; c < 8; c++) { row[c ^ sw] = x[c]; xp[tid * XLD + c] = x[c]; }
+      for (int c = 0; c < 8; c++) row[c ^ sw] = x[c];
     }
     __syncthreads();
     // (3) trailing update on 8x8 tiles: C[ti][tj] -= X_ti X_tj^T.  Balanced static schedule: tile-rows a and
     // b = nt-1-a together hold nt+1 tiles (nt <= 15 -> at most 8 pairs); with 8 warps each warp takes one pair,
     // with 16 warps two warps share a pair.
-    const int nt = 15 - p, rb = c0 + 8, rbt = p + 1;
+    const int nt = 15 - p, rbt = p + 1;
     {
       const int a_row = P2_WARPS == 8 ? warp : warp >> 1, b_row = nt - 1 - a_row;
       if (a_row <= b_row) {
@@ -226,14 +282,16 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
           const int pb_ = two ? pos + 1 : pos;
           const int ti0 = pos < na ? a_row : b_row, tj0 = pos < na ? pos : pos - na;
           const int ti1 = pb_ < na ? a_row : b_row, tj1 = pb_ < na ? pb_ : pb_ - na;
-          const double* xa_0 = xp + (rb + 8 * ti0 + g) * XLD + q;
-          const double* xa_1 = xp + (rb + 8 * ti1 + g) * XLD + q;
-          const double* xb_0 = xp + (rb + 8 * tj0 + g) * XLD + q;
-          const double* xb_1 = xp + (rb + 8 * tj1 + g) * XLD + q;
+          // panel fragments straight from the tiles of block column p (row g, columns q and q+4: the
+          // swizzle makes the second one the first XOR 4)
+          const double* xa_0 = sm + tile_base(rbt + ti0, p) + x_in;
+          const double* xa_1 = sm + tile_base(rbt + ti1, p) + x_in;
+          const double* xb_0 = sm + tile_base(rbt + tj0, p) + x_in;
+          const double* xb_1 = sm + tile_base(rbt + tj1, p) + x_in;
           double2* cp0 = reinterpret_cast<double2*>(sm + tile_base(rbt + ti0, rbt + tj0) + c_in);
           double2* cp1 = reinterpret_cast<double2*>(sm + tile_base(rbt + ti1, rbt + tj1) + c_in);
-          const double a00 = -xa_0[0], a01 = -xa_0[4], a10 = -xa_1[0], a11 = -xa_1[4];
-          const double b00 = xb_0[0], b01 = xb_0[4], b10 = xb_1[0], b11 = xb_1[4];
+          const double a00 = -xa_0[0], a01 = -xa_0[x4], a10 = -xa_1[0], a11 = -xa_1[x4];
+          const double b00 = xb_0[0], b01 = xb_0[x4], b10 = xb_1[0], b11 = xb_1[x4];
           double2 c0v = *cp0, c1v = *cp1;
           double2 p0 = make_double2(0.0, 0.0), p1 = make_double2(0.0, 0.0);
           dmma(c0v.x, c0v.y, a00, b00);
