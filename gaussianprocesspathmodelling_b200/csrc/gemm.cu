@@ -83,6 +83,31 @@ __device__ __forceinline__ OpDesc make_op(const GemmArgs& p, const TileCoord& tc
   return d;
 }
 
+// One slab (16 contraction steps) of a warp's 64 x 32 tile: 8 x 4 sub-tiles of 8 x 8, DMMA.8x8x4.  Sub-tile
+// (mt, nt) is computed iff nt <= mt + D; D = 8 keeps all of them, D = 0 / -4 are the two staircase shapes a warp
+// sees on a symmetric diagonal tile (GemmArgs::diag_lower).
+template <int D>
+__device__ __forceinline__ void slab_mma(double (&acc)[8][4][2], uint32_t sa, uint32_t sb, const uint32_t (&off)[4]) {
+#pragma unroll
+  for (int k4 = 0; k4 < 4; k4++) {
+    double a[8], b[4];
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++)
+      if (mt + D >= 0) a[mt] = lds_f64(sa + mt * 1024 + off[k4]);
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+      if (nt <= 7 + D) b[nt] = lds_f64(sb + nt * 1024 + off[k4]);
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++)
+        if (nt <= mt + D) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+  }
+}
+
+// DG: instantiation with the diag_lower staircase paths (the plain one keeps the variance sweep's inner loop
+// free of the extra branches)
+template <bool DG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapB2,
@@ -189,6 +214,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t a_warp = wm * 64 * 128, b_warp = SLAB_BYTES + wn * 32 * 128;
   const long long rows_end = p.c_rows_end + bz * p.batch_c_rows;
   int sg = 0, ct = 0;
+  // Symmetric diagonal tiles (diag_lower): sub-tile (mt, nt) of this warp lies on or below the diagonal iff
+  // nt <= mt + dd with dd = 8 wm - 4 wn.  dd >= 3: all kept; dd = 0 / -4: staircases of 26 / 10 sub-tiles;
+  // dd <= -8: none.  With the column-group reversal above every scheduler keeps 32 or 36 of its 64 sub-tiles.
+  const int dd = 8 * wm - 4 * wn;
+  const int dcode = dd >= 3 ? 0 : (dd == 0 ? 1 : (dd == -4 ? 2 : 3));
 
   for (int t = t_begin; t < t_end; t++) {
     const TileCoord tc = tile_coord(p, tile_id(t));
@@ -196,6 +226,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int o = 0; o < nops; o++) {
       const OpDesc d = make_op(p, tc, o, bz);
       const bool sub = d.epi == EPI_SUB;
+      const int dsel = (DG && tc.ti == tc.tj) ? dcode : 0;
       double acc[8][4][2];
 #pragma unroll
       for (int mt = 0; mt < 8; mt++)
@@ -207,19 +238,12 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(bar_full + st * 8, (sg / STAGES) & 1);
         const uint32_t sa = (d.a_smem ? cbuf + s * SLAB_BYTES : base + st * 2 * SLAB_BYTES) + a_warp;
         const uint32_t sb = base + st * 2 * SLAB_BYTES + b_warp;
-        if (!d.tri_b || s <= 2 * wn + 1) {
-#pragma unroll
-        for (int k4 = 0; k4 < 4; k4++) {
-          double a[8], b[4];
-#pragma unroll
-          for (int mt = 0; mt < 8; mt++) a[mt] = lds_f64(sa + mt * 1024 + off[k4]);
-#pragma unroll
-          for (int nt = 0; nt < 4; nt++) b[nt] = lds_f64(sb + nt * 1024 + off[k4]);
-#pragma unroll
-          for (int mt = 0; mt < 8; mt++)
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
-        }
+        if (dsel == 0) {
+          if (!d.tri_b || s <= 2 * wn + 1) slab_mma<8>(acc, sa, sb, off);
+        } else if (dsel == 1) {
+          slab_mma<0>(acc, sa, sb, off);
+        } else if (dsel == 2) {
+          slab_mma<-4>(acc, sa, sb, off);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + st * 8);
@@ -314,7 +338,8 @@ int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& 
                 const CUtensorMap* mapB2) {
   static bool attr_set = false;
   if (!attr_set) {
-    GPM_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    GPM_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    GPM_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     attr_set = true;
   }
   GemmArgs args = args_in;
@@ -345,7 +370,10 @@ int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& 
   if (args.sweep_tri || args.kstart_mode || args.kend_mode) best_c = 1;   // tiles differ in work: let the hardware balance them
   args.tiles_per_cta = best_c;
   dim3 grid(args.sweep_tri ? (total + 1) / 2 : (total + best_c - 1) / best_c, batch);
-  gemm_nt_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(mapA, mapB, mapC, mapB2 ? *mapB2 : mapB, args);
+  if (args.diag_lower)
+    gemm_nt_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(mapA, mapB, mapC, mapB2 ? *mapB2 : mapB, args);
+  else
+    gemm_nt_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(mapA, mapB, mapC, mapB2 ? *mapB2 : mapB, args);
   GPM_LAUNCH_CHECK();
   return 0;
 }

@@ -40,6 +40,8 @@ struct GemmArgs {
   long long batch_cols;   // columns added per batch index to the A, B and C column origins
   int tiles_per_cta;      // filled by launch_gemm: consecutive tiles one CTA works through
   int max_tiles_per_cta;  // 0 = default (16); the look-ahead Cholesky caps it so that SMs free up regularly
+  int diag_lower;         // tile mode: tiles with ti == tj are symmetric (SYRK) and only their lower triangle is
+                          // needed: the 8x8 sub-tiles strictly above the diagonal are not computed
 };
 
 // number of CTAs along x for the given args

@@ -142,11 +142,20 @@ __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
   bool ok[PER_WARP];
 #pragma unroll
   for (int e = 0; e < PER_WARP; e++) {
-    const int t = warp + P2_WARPS * e;
+    // Tile (ta, tb) costs 2(TB - tb) DMMAs in phase 1 and 2(ta + 1) in phase 2, so tiles are handed out in
+    // balanced pairs {(a, b), (TB-1-a, TB-1-b)} and {(a, TB-1-b), (TB-1-a, b)}: every warp gets the same work.
+    const int t = warp * PER_WARP + e;
     ok[e] = t < TILES;
     const int tt = ok[e] ? t : 0;
-    const int pair = tt / (TB * TB);
-    ta[e] = (tt / TB) % TB; tb[e] = tt % TB;
+    const int pair = tt / (TB * TB), u = tt % (TB * TB);
+    if (TB >= 2) {
+      constexpr int H = TB >= 2 ? TB / 2 : 1;
+      const int quad = u >> 2, m = u & 3, a = quad / H, b = quad % H;
+      ta[e] = (m & 1) ? TB - 1 - a : a;
+      tb[e] = (m == 1 || m == 2) ? TB - 1 - b : b;
+    } else {
+      ta[e] = 0; tb[e] = 0;
+    }
     t1[e] = pair * 2 * TB;
     c0[e] = c1[e] = 0.0;
   }
@@ -194,6 +203,19 @@ __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
   __syncthreads();
 }
 
+#ifdef GPM_POTF2_TIMING
+// phase stamps of CTA 0 (cycles): the branch on a value loaded from shared memory after the barrier keeps
+// the clock read behind the barrier's completion (BAR.SYNC.DEFER_BLOCKING lets independent work issue early)
+__device__ long long g_p2_marks[64];
+#define P2_MARK(slot)                                                                        \
+  if (tid == 0 && blockIdx.x == 0) {                                                         \
+    const double pv_ = *reinterpret_cast<volatile double*>(sm + PACKED + 63);                \
+    if (__double_as_longlong(pv_) != 0x7ff8dead0000beefLL) g_p2_marks[slot] = clock64();     \
+  }
+#else
+#define P2_MARK(slot)
+#endif
+
 // Factor diagonal block kblk of K in shared memory, write L_kk back and inv(L_kk) to invD.
 // Rows/columns beyond N are padded with the identity.  blockIdx.x = batch index.
 //
@@ -202,7 +224,7 @@ __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
 // the rank-8 update to the trailing 8x8 tiles with DMMA.8x8x4 on a static balanced schedule.  The
 // 128x128 inverse is then assembled from the 8x8 diagonal inverses by recursive doubling, also on
 // DMMA tiles.  The kernel is latency-bound (serial pivot chain, barrier hand-offs), so it is sized
-// for two CTAs per SM (83 KB shared memory, 256 threads): batched fits keep both busy.
+// for three CTAs per SM (71 KB shared memory, 256 threads): batched fits keep all of them busy.
 template <int P2_THREADS>
 __global__ void __launch_bounds__(P2_THREADS, P2_THREADS == 256 ? 3 : 1)
 potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, double* __restrict__ invD,
@@ -218,37 +240,42 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
   const long long r0 = (long long)kblk * NB;
   const int nv = (int)((N - r0) < NB ? (N - r0) : NB);
 
-  // load the lower triangle (16 independent loads in flight per thread); identity padding beyond nv
-  for (int u0 = 0; u0 < NB * NB / P2_THREADS; u0 += 16) {
-    double v[16];
+  // load the lower triangle as 16-byte pairs (LU independent loads in flight per thread); identity padding
+  // beyond nv.  A pair never straddles a tile and keeps its order under the in-tile swizzle (bit 2 only).
+  constexpr int LU = P2_THREADS == 256 ? 8 : 16;   // loads in flight per thread (register budget)
+  for (int u0 = 0; u0 < NB * NB / 2 / P2_THREADS; u0 += LU) {
+    double2 v[LU];
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
-      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 7, c = idx & 127;
-      const bool in = (i < nv) && (c <= i);
-      v[u] = in ? K[(r0 + i) * ldk + r0 + c] : ((i == c && i >= nv) ? 1.0 : 0.0);
+    for (int u = 0; u < LU; u++) {
+      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 6, c = (idx & 63) * 2;
+      if (i < nv && c <= i) v[u] = *reinterpret_cast<const double2*>(K + (r0 + i) * ldk + r0 + c);
+      else v[u] = make_double2((i == c && i >= nv) ? 1.0 : 0.0, (i == c + 1 && i >= nv) ? 1.0 : 0.0);
     }
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
-      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 7, c = idx & 127;
-      if ((c >> 3) <= (i >> 3)) sm[toff(i, c)] = v[u];
+    for (int u = 0; u < LU; u++) {
+      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 6, c = (idx & 63) * 2;
+      if ((c >> 3) <= (i >> 3)) *reinterpret_cast<double2*>(sm + toff(i, c)) = v[u];
     }
   }
+  P2_MARK(0)
   __syncthreads();
+  P2_MARK(1)
 
   const int g = lane >> 2, q = lane & 3;
   const int c_in = g * 8 + ((2 * q) ^ (((g >> 1) & 1) << 2));
   const int x_in = g * 8 + (q ^ (((g >> 1) & 1) << 2));          // panel fragment: row g, column q
   const int x4 = (x_in ^ 4) - x_in;                               // ... and column q + 4
+  constexpr int UW = P2_WARPS - 1;                                // update warps; warp UW looks ahead
+  if (tid == 0) {
+    const int bad = chol8_tile(sm, tile_base(0, 0), l8, rd);
+    if (bad && bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + bad));
+  }
+  __syncthreads();
   for (int p = 0; p < 16; p++) {
     const int c0 = 8 * p;
-    // (1) 8x8 diagonal block: factor in one thread
-    if (tid == 0) {
-      const int bad = chol8_tile(sm, tile_base(p, p), l8, rd + c0);
-      if (bad && c0 + bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + c0 + bad));
-    }
-    __syncthreads();
-    // (2) panel solve by forward substitution, one thread per row below the block:
-    //     x_c = (a_c - sum_{k<c} x_k L8[c][k]) / L8[c][c]
+    P2_MARK(2 + 3 * p)
+    // (1) panel solve by forward substitution against the factored 8x8 diagonal tile (l8, rd), one thread
+    //     per row below it:  x_c = (a_c - sum_{k<c} x_k L8[c][k]) / L8[c][c]
     if (tid < NB && tid >= c0 + 8) {
       double x[8];
       double* row = sm + tile_base(tid >> 3, p) + (tid & 7) * 8;
@@ -265,56 +292,87 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
       for (int c = 0; c < 8; c++) row[c ^ sw] = x[c];
     }
     __syncthreads();
-    // (3) trailing update on 8x8 tiles: C[ti][tj] -= X_ti X_tj^T.  Balanced static schedule: tile-rows a and
-    // b = nt-1-a together hold nt+1 tiles (nt <= 15 -> at most 8 pairs); with 8 warps each warp takes one pair,
-    // with 16 warps two warps share a pair.
+    P2_MARK(3 + 3 * p)
+    if (p == 15) break;
+    // (2) rank-8 update of the trailing 8x8 tiles, C[ti][tj] -= X_ti X_tj^T (DMMA), with look-ahead: the last
+    //     warp updates the next diagonal tile first and factors it (one lane) while the other warps update
+    //     the remaining tiles, so the serial 8x8 factorisation leaves the critical path of the big panels.
     const int nt = 15 - p, rbt = p + 1;
-    {
-      const int a_row = P2_WARPS == 8 ? warp : warp >> 1, b_row = nt - 1 - a_row;
-      if (a_row <= b_row) {
-        const int na = a_row + 1;
-        const int run = (a_row == b_row) ? na : nt + 1;
-        const int halfn = P2_WARPS == 8 ? run : (run + 1) >> 1;
-        const int pos0 = P2_WARPS == 8 ? 0 : (warp & 1) * halfn;
-        const int total = min(run, pos0 + halfn);
-        for (int pos = pos0; pos < total; pos += 2) {
-          const bool two = pos + 1 < total;
-          const int pb_ = two ? pos + 1 : pos;
-          const int ti0 = pos < na ? a_row : b_row, tj0 = pos < na ? pos : pos - na;
-          const int ti1 = pb_ < na ? a_row : b_row, tj1 = pb_ < na ? pb_ : pb_ - na;
-          // panel fragments straight from the tiles of block column p (row g, columns q and q+4: the
-          // swizzle makes the second one the first XOR 4)
-          const double* xa_0 = sm + tile_base(rbt + ti0, p) + x_in;
-          const double* xa_1 = sm + tile_base(rbt + ti1, p) + x_in;
-          const double* xb_0 = sm + tile_base(rbt + tj0, p) + x_in;
-          const double* xb_1 = sm + tile_base(rbt + tj1, p) + x_in;
-          double2* cp0 = reinterpret_cast<double2*>(sm + tile_base(rbt + ti0, rbt + tj0) + c_in);
-          double2* cp1 = reinterpret_cast<double2*>(sm + tile_base(rbt + ti1, rbt + tj1) + c_in);
-          const double a00 = -xa_0[0], a01 = -xa_0[x4], a10 = -xa_1[0], a11 = -xa_1[x4];
-          const double b00 = xb_0[0], b01 = xb_0[x4], b10 = xb_1[0], b11 = xb_1[x4];
-          double2 c0v = *cp0, c1v = *cp1;
-          double2 p0 = make_double2(0.0, 0.0), p1 = make_double2(0.0, 0.0);
-          dmma(c0v.x, c0v.y, a00, b00);
-          dmma(p0.x, p0.y, a01, b01);
-          dmma(c1v.x, c1v.y, a10, b10);
-          dmma(p1.x, p1.y, a11, b11);
-          c0v.x += p0.x; c0v.y += p0.y;
-          *cp0 = c0v;
-          if (two) { c1v.x += p1.x; c1v.y += p1.y; *cp1 = c1v; }
+    const int T = nt * (nt + 1) / 2;             // trailing tiles in row-major lower order; tile 0 = (rbt, rbt)
+    if (warp == UW) {
+      const double* xa = sm + tile_base(rbt, p) + x_in;
+      double2* cp = reinterpret_cast<double2*>(sm + tile_base(rbt, rbt) + c_in);
+      const double b0 = xa[0], b1 = xa[x4];
+      double2 c = *cp;
+      dmma(c.x, c.y, -b0, b0);
+      dmma(c.x, c.y, -b1, b1);
+      *cp = c;
+      __syncwarp();
+      if (lane == 0) {
+        const int bad = chol8_tile(sm, tile_base(rbt, rbt), l8, rd + c0 + 8);
+        if (bad && c0 + 8 + bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + c0 + 8 + bad));
+      }
+    } else {
+      // contiguous chunk of tiles per warp: consecutive tiles share their row, so the A fragments are
+      // reloaded only at a row change and the C / B addresses advance by constant strides
+      const int per = (T - 1 + UW - 1) / UW;
+      int t = 1 + warp * per;
+      const int tend = min(T, t + per);
+      if (t < tend) {
+        int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+        while (ti * (ti + 1) / 2 > t) ti--;
+        int tj = t - ti * (ti + 1) / 2;
+        const int bb0 = tile_base(rbt, p) + x_in;
+        int cb = tile_base(rbt + ti, rbt + tj) + c_in;      // C fragment of tile (ti, tj)
+        int bb = tile_base(rbt + tj, p) + x_in;             // B fragment: panel rows of tile-row tj
+        double a0, a1;
+        { const double* xa = sm + tile_base(rbt + ti, p) + x_in; a0 = -xa[0]; a1 = -xa[x4]; }
+        auto step = [&]() {
+          tj++; cb += 64; bb += (rbt + tj) * 64;
+          if (tj > ti) {
+            ti++; tj = 0;
+            cb = tile_base(rbt + ti, rbt) + c_in; bb = bb0;
+            const double* xa = sm + tile_base(rbt + ti, p) + x_in; a0 = -xa[0]; a1 = -xa[x4];
+          }
+        };
+        while (t < tend) {
+          const bool two = t + 1 < tend;
+          const int cbA = cb, bbA = bb;
+          const double aA0 = a0, aA1 = a1;
+          if (two) step();
+          const int cbB = cb, bbB = bb;
+          const double aB0 = a0, aB1 = a1;
+          if (t + 2 < tend) step();
+          t += 2;
+          double2 cA = *reinterpret_cast<const double2*>(sm + cbA), cB = *reinterpret_cast<const double2*>(sm + cbB);
+          const double bA0 = sm[bbA], bA1 = sm[bbA + x4], bB0 = sm[bbB], bB1 = sm[bbB + x4];
+          dmma(cA.x, cA.y, aA0, bA0);
+          dmma(cB.x, cB.y, aB0, bB0);
+          dmma(cA.x, cA.y, aA1, bA1);
+          dmma(cB.x, cB.y, aB1, bB1);
+          *reinterpret_cast<double2*>(sm + cbA) = cA;
+          if (two) *reinterpret_cast<double2*>(sm + cbB) = cB;
         }
       }
     }
     __syncthreads();
+    P2_MARK(4 + 3 * p)
   }
 
-  // ---- write L_kk (lower part, valid rows) ----
-  for (int u0 = 0; u0 < NB * NB / P2_THREADS; u0 += 16) {
+  // ---- write L_kk (lower part, valid rows), 16-byte pairs ----
+  for (int u0 = 0; u0 < NB * NB / 2 / P2_THREADS; u0 += 16) {
 #pragma unroll
     for (int u = 0; u < 16; u++) {
-      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 7, c = idx & 127;
-      if (c <= i && i < nv) K[(r0 + i) * ldk + r0 + c] = sm[toff(i, c)];
+      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 6, c = (idx & 63) * 2;
+      if (i < nv && c <= i) {
+        const double2 v = *reinterpret_cast<const double2*>(sm + toff(i, c));
+        double* dst = K + (r0 + i) * ldk + r0 + c;
+        if (c < i) *reinterpret_cast<double2*>(dst) = v; else *dst = v.x;
+      }
     }
   }
+  P2_MARK(50)
   // ---- inverse, level 0: the sixteen 8x8 diagonal blocks, one thread per column ----
   double xcol[8];
   {
@@ -339,18 +397,25 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
     for (int i = 0; i < 8; i++) Lb[in_tile(i, j)] = xcol[i];
   }
   __syncthreads();
+  P2_MARK(51)
   inv_level_dmma<8, P2_WARPS>(sm, warp, lane);
+  P2_MARK(52)
   inv_level_dmma<16, P2_WARPS>(sm, warp, lane);
+  P2_MARK(53)
   inv_level_dmma<32, P2_WARPS>(sm, warp, lane);
+  P2_MARK(54)
   inv_level_dmma<64, P2_WARPS>(sm, warp, lane);
+  P2_MARK(55)
 
-  for (int u0 = 0; u0 < NB * NB / P2_THREADS; u0 += 16) {
+  for (int u0 = 0; u0 < NB * NB / 2 / P2_THREADS; u0 += 16) {
 #pragma unroll
     for (int u = 0; u < 16; u++) {
-      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 7, c = idx & 127;
-      invD[idx] = ((c >> 3) <= (i >> 3)) ? sm[toff(i, c)] : 0.0;
+      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 6, c = (idx & 63) * 2;
+      reinterpret_cast<double2*>(invD)[idx] =
+          ((c >> 3) <= (i >> 3)) ? *reinterpret_cast<const double2*>(sm + toff(i, c)) : make_double2(0.0, 0.0);
     }
   }
+  P2_MARK(56)
 }
 
 __global__ void zero_info_kernel(int* info, int n) {
@@ -440,6 +505,7 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
     a.a_col0 = k0 * NB; a.b_col0 = k0 * NB; a.b_tile_rows = NB; a.klen = kw * NB;
     a.c_rows_end = N; a.c_cols_end = N;
     a.epi = EPI_SUB;
+    a.diag_lower = 1;                           // tile (0,0) / tiles ti == tj are L L^T: lower triangle only
     a.batch_a_rows = batch_rows; a.batch_b_rows = batch_rows; a.batch_c_rows = batch_rows;
     if (jhi - jlo == 1) {                       // a single tile column: rows jlo .. nblk-1
       a.tri = 0; a.tiles_m = nblk - jlo; a.tiles_n = 1;
@@ -519,6 +585,12 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
 }  // namespace gpm
 
 using namespace gpm;
+
+#ifdef GPM_POTF2_TIMING
+extern "C" int gpm_debug_potf2_marks(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_p2_marks, sizeof(long long) * 64);
+}
+#endif
 
 extern "C" size_t gpm_potrf_workspace_bytes(int64_t N) {
   if (N <= 0) return 0;
