@@ -1,6 +1,8 @@
 // Batched per-path fits: B independent paths of equal length N.  All paths advance together
 // through batched launches (grid.y = path) of the same kernels the single-matrix path uses:
 // covariance (lower tiles) -> blocked Cholesky with look-ahead -> blocked solves -> LML.
+#include <stdlib.h>
+
 #include "gemm.cuh"
 
 namespace gpm {
@@ -9,12 +11,14 @@ int launch_cov(const double* X, long long N, int D, const Theta& th, double* K, 
                int lower_only, int batch, long long batch_x, long long batch_k, cudaStream_t stream,
                const double* theta_dev, int theta_stride);
 int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, double* invD, int* info,
-                  int batch, long long batch_rows, cudaStream_t s0);
+                  int batch, long long batch_rows, cudaStream_t s0, double* rhs_r, double* rhs_z, int R,
+                  long long batch_rhs_rows);
+bool solve_paths_supported(long long N);
 int solve_blocked(const double* L, long long N, long long ldl, const double* invD, double* alpha, int R,
                   int batch, long long batch_l, long long batch_inv, long long batch_z, cudaStream_t stream);
 int solve_paths(const double* L, long long N, long long ldl, const double* invD, const double* Y,
                 double* alpha, double* lml, int R, int batch, long long batch_l, long long batch_inv,
-                long long batch_y, cudaStream_t stream);
+                long long batch_y, cudaStream_t stream, const double* zfwd);
 int launch_lml(const double* L, long long N, long long ldl, const double* Y, const double* alpha, int R,
                double* lml, int batch, long long batch_l, long long batch_y, cudaStream_t stream);
 
@@ -27,7 +31,7 @@ using namespace gpm;
 extern "C" size_t gpm_fit_batched_workspace_bytes(int64_t B, int64_t N) {
   if (B <= 0 || N <= 0) return 0;
   const long long np = round_up_ll(N, NB);
-  return (size_t)B * (size_t)(np * np + np * NB + 8) * sizeof(double);   // + per-path theta
+  return (size_t)B * (size_t)(np * np + np * NB + 8 + np * 8) * sizeof(double);   // + per-path theta + z = L^{-1} Y
 }
 
 extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const double* Yb, int64_t B, int64_t N,
@@ -60,8 +64,17 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
     theta_dev = tdev;
   }
   if ((rc = launch_cov(Xb, N, D, th, Kb, np, 1, (int)B, N * D, np * np, st, theta_dev, (int)theta_stride))) return rc;
-  if ((rc = potrf_blocked(h, Kb, N, np, invD, info, (int)B, np, st))) return rc;
-  rc = solve_paths(Kb, N, np, invD, Yb, alpha, lml, R, (int)B, np * np, (long long)nblk * NB * NB, N * R, st);
+  // Paths short enough for the one-CTA-per-path solve: the forward substitution rides along with the
+  // factorisation (alpha holds the running residual, zf receives z = L^{-1} Y), and the solve kernel only
+  // runs the backward pass.
+  if (solve_paths_supported(N) && getenv("GPM_NO_FUSED_FWD") == nullptr) {
+    double* zf = invD + (long long)B * nblk * NB * NB + (long long)B * 8;
+    GPM_CUDA(cudaMemcpyAsync(alpha, Yb, (size_t)B * N * R * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if ((rc = potrf_blocked(h, Kb, N, np, invD, info, (int)B, np, st, alpha, zf, R, N))) return rc;
+    return solve_paths(Kb, N, np, invD, Yb, alpha, lml, R, (int)B, np * np, (long long)nblk * NB * NB, N * R, st, zf);
+  }
+  if ((rc = potrf_blocked(h, Kb, N, np, invD, info, (int)B, np, st, nullptr, nullptr, 0, 0))) return rc;
+  rc = solve_paths(Kb, N, np, invD, Yb, alpha, lml, R, (int)B, np * np, (long long)nblk * NB * NB, N * R, st, nullptr);
   if (rc >= 0) return rc;
   GPM_CUDA(cudaMemcpyAsync(alpha, Yb, (size_t)B * N * R * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if ((rc = solve_blocked(Kb, N, np, invD, alpha, R, (int)B, np * np, (long long)nblk * NB * NB, N * R, st))) return rc;

@@ -83,6 +83,13 @@ __device__ __forceinline__ OpDesc make_op(const GemmArgs& p, const TileCoord& tc
   return d;
 }
 
+#ifdef GPM_GEMM_TIMING
+__device__ long long g_gemm_marks[8 * 16];
+#define GM_MARK(slot) if (DG && p.rhs_r != nullptr && blockIdx.y == 7 && lane == 0 && (warp == 0 || warp == 7)) g_gemm_marks[(warp ? 64 : 0) + (t - t_begin) * 16 + (slot)] = clock64();
+#else
+#define GM_MARK(slot)
+#endif
+
 // One slab (16 contraction steps) of a warp's 64 x 32 tile: 8 x 4 sub-tiles of 8 x 8, DMMA.8x8x4.  Sub-tile
 // (mt, nt) is computed iff nt <= mt + D; D = 8 keeps all of them, D = 0 / -4 are the two staircase shapes a warp
 // sees on a symmetric diagonal tile (GemmArgs::diag_lower).
@@ -105,8 +112,8 @@ __device__ __forceinline__ void slab_mma(double (&acc)[8][4][2], uint32_t sa, ui
   }
 }
 
-// DG: instantiation with the diag_lower staircase paths (the plain one keeps the variance sweep's inner loop
-// free of the extra branches)
+// DG: instantiation for the factorisation (diag_lower staircase paths, fused forward substitution); the plain
+// one keeps the variance sweep's loops free of the extra branches
 template <bool DG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -220,18 +227,28 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int dd = 8 * wm - 4 * wn;
   const int dcode = dd >= 3 ? 0 : (dd == 0 ? 1 : (dd == -4 ? 2 : 3));
 
+  int rhs_tiles = 0;
+  if (DG && p.rhs_r != nullptr) {
+    // z_k is the same for every tile of this launch and matrix: stage it once; the C-tile buffer is free in
+    // an EPI_STORE launch.  The loads overlap the first tile's main loop.
+    const double* zk = p.rhs_z + (p.rhs_z_row0 + bz * p.batch_rhs_rows) * p.rhs_R;
+    for (int idx = tid; idx < NB * p.rhs_R; idx += CONSUMER_WARPS * 32) red[idx] = zk[idx];
+    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
+  }
+
   for (int t = t_begin; t < t_end; t++) {
     const TileCoord tc = tile_coord(p, tile_id(t));
     const int nops = ops_of(tc);
     for (int o = 0; o < nops; o++) {
       const OpDesc d = make_op(p, tc, o, bz);
       const bool sub = d.epi == EPI_SUB;
-      const int dsel = (DG && tc.ti == tc.tj) ? dcode : 0;
+      const int dsel = (DG && p.diag_lower && tc.ti == tc.tj) ? dcode : 0;
       double acc[8][4][2];
 #pragma unroll
       for (int mt = 0; mt < 8; mt++)
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+      GM_MARK(0)
 
       for (int s = 0; s < d.nslab; s++, sg++) {
         const int st = sg % STAGES;
@@ -249,6 +266,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) mbar_arrive(bar_empty + st * 8);
       }
 
+      GM_MARK(1)
       // ===== epilogue: registers (-> C from smem) -> global, 16-byte stores =====
       const long long crow_base = p.c_row0 + (long long)tc.ti * NB + wm * 64 + bz * p.batch_c_rows;
       const long long ccol_base = d.c_col + wn * 32 + 2 * q;
@@ -321,6 +339,59 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
       }
+      GM_MARK(2)
+      if (DG && p.rhs_r != nullptr) {
+        // fused forward substitution: r_i -= L_ik z_k with the tile still in the accumulators (z_k was staged
+        // in shared memory before the main loop).  Partial sums per (row, column group) go through shared
+        // memory and are added in a fixed order; the two partial-sum buffers alternate between tiles so that
+        // one barrier per tile suffices, and the residual is updated with a fire-and-forget reduction (one
+        // addition per element and launch, so the result does not depend on timing).
+        const int R = p.rhs_R;
+        const double* zsm = red;                                   // [128][R]
+        double* psm = red + NB * 8 + (rhs_tiles & 1) * (NB * 4 * 8);   // [128][4][R], double-buffered
+        rhs_tiles++;
+        for (int r = 0; r < R; r++) {
+          // this thread's 8 entries of z_k (columns 2q, 2q+1 of each of its 4 sub-tile columns), loaded once;
+          // then eight independent accumulation chains, one per sub-tile row
+          double zv[4][2], sum[8];
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            const int col = wn * 32 + nt * 8 + 2 * q;
+            zv[nt][0] = zsm[col * R + r];
+            zv[nt][1] = zsm[(col + 1) * R + r];
+          }
+#pragma unroll
+          for (int mt = 0; mt < 8; mt++) sum[mt] = 0.0;
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int mt = 0; mt < 8; mt++) {
+              sum[mt] = fma(acc[mt][nt][0], zv[nt][0], sum[mt]);
+              sum[mt] = fma(acc[mt][nt][1], zv[nt][1], sum[mt]);
+            }
+#pragma unroll
+          for (int mt = 0; mt < 8; mt++) sum[mt] += __shfl_xor_sync(0xffffffffu, sum[mt], 1);
+#pragma unroll
+          for (int mt = 0; mt < 8; mt++) sum[mt] += __shfl_xor_sync(0xffffffffu, sum[mt], 2);
+          if (q == 0) {
+#pragma unroll
+            for (int mt = 0; mt < 8; mt++) psm[((wm * 64 + mt * 8 + g) * 4 + wn) * R + r] = sum[mt];
+          }
+        }
+        GM_MARK(3)
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
+        GM_MARK(4)
+        if (tid < NB) {
+          const long long row = p.rhs_r_row0 + (long long)tc.ti * NB + tid;
+          if (row < p.rhs_rows_end) {
+            double* rr = p.rhs_r + (row + bz * p.batch_rhs_rows) * R;
+            for (int r = 0; r < R; r++)
+              atomicAdd(rr + r, -((psm[(tid * 4 + 0) * R + r] + psm[(tid * 4 + 1) * R + r]) +
+                                  (psm[(tid * 4 + 2) * R + r] + psm[(tid * 4 + 3) * R + r])));
+          }
+        }
+        GM_MARK(5)
+      }
       if (d.signal) {
         // publish this op's global stores to the async proxy (TMA) before the producer loads them; this also
         // tells the producer that the C-tile buffer (operand + row-sum scratch of this op) is free again
@@ -332,6 +403,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   }
 }
+
+#ifdef GPM_GEMM_TIMING
+extern "C" int gpm_debug_gemm_marks(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_gemm_marks, sizeof(long long) * 128);
+}
+#endif
+}  // namespace gpm
+namespace gpm {
 
 int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& mapB,
                 const CUtensorMap& mapC, const GemmArgs& args_in, int batch, cudaStream_t stream,
@@ -349,6 +428,10 @@ int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& 
   }
   if (args.klen <= 0 || args.klen % SLAB_K != 0) {
     set_error("gemm: contraction length %d is not a positive multiple of %d", args.klen, SLAB_K);
+    return 998;
+  }
+  if (args.rhs_r && (args.epi != EPI_STORE || args.rowsq || args.sweep_nblk > 0 || args.rhs_R < 1 || args.rhs_R > 8)) {
+    set_error("gemm: the fused forward substitution needs a plain EPI_STORE tile launch with 1 <= R <= 8");
     return 998;
   }
   if (args.sweep_nblk == 0 && args.epi == EPI_SUB && args.rowsq) {
@@ -370,7 +453,7 @@ int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& 
   if (args.sweep_tri || args.kstart_mode || args.kend_mode) best_c = 1;   // tiles differ in work: let the hardware balance them
   args.tiles_per_cta = best_c;
   dim3 grid(args.sweep_tri ? (total + 1) / 2 : (total + best_c - 1) / best_c, batch);
-  if (args.diag_lower)
+  if (args.diag_lower || args.rhs_r)
     gemm_nt_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(mapA, mapB, mapC, mapB2 ? *mapB2 : mapB, args);
   else
     gemm_nt_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(mapA, mapB, mapC, mapB2 ? *mapB2 : mapB, args);

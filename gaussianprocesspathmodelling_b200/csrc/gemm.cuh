@@ -40,6 +40,17 @@ struct GemmArgs {
   long long batch_cols;   // columns added per batch index to the A, B and C column origins
   int tiles_per_cta;      // filled by launch_gemm: consecutive tiles one CTA works through
   int max_tiles_per_cta;  // 0 = default (16); the look-ahead Cholesky caps it so that SMs free up regularly
+  // tile mode, EPI_STORE: forward substitution fused into the panel solves of a factorisation.  After the tile
+  // L_ik = K_ik inv(L_kk)^T is formed (still in registers) the running right-hand side is updated,
+  //   r_i -= L_ik z_k,   z_k = inv(L_kk) r_k  (written by potf2 before this launch),
+  // so the forward solve needs no pass of its own over L.  rhs_r / rhs_z: (rows x rhs_R) row-major.
+  double* rhs_r;
+  const double* rhs_z;
+  int rhs_R;
+  long long rhs_z_row0;   // first row of z_k
+  long long rhs_r_row0;   // first row of the residual block of tile ti = 0
+  long long rhs_rows_end; // rows per matrix (exclusive bound for the residual rows)
+  long long batch_rhs_rows;
   int diag_lower;         // tile mode: tiles with ti == tj are symmetric (SYRK) and only their lower triangle is
                           // needed: the 8x8 sub-tiles strictly above the diagonal are not computed
 };

@@ -20,7 +20,7 @@ namespace gpm {
 
 constexpr int NT8 = NB / 8;                         // 16 tiles per block edge
 constexpr int PACKED = NT8 * (NT8 + 1) / 2 * 64;    // doubles in the packed lower triangle (136 tiles)
-constexpr int POTF2_SMEM = (PACKED + 64 + NB) * 8;  // 69.5 KB + 1.5 KB: three CTAs per SM
+constexpr int POTF2_SMEM = (PACKED + 64 + NB + 4 * NB) * 8;  // 69.5 KB + 5.5 KB: three CTAs per SM (<= 75 KB each)
 
 // The 128x128 diagonal block lives in shared memory as its lower triangle of 8x8 tiles (tile (ti,tj),
 // tj <= ti, at index ti(ti+1)/2 + tj, 64 contiguous doubles, row-major).  Inside a tile the column is
@@ -129,25 +129,31 @@ __device__ __forceinline__ int chol8_tile(double* sm, int tb0, double* l8, doubl
 
 // One level of the recursive-doubling inverse on DMMA tiles:  X21 = -X22 * (L21 * X11)  for all
 // 64/S pairs of SxS diagonal blocks (X11, X22 already inverted in place, upper parts zero).
-// The contraction loop is outermost so that a warp keeps PER_WARP independent DMMA chains in flight.
-// Only tiles on or below the diagonal are touched (they are the only ones stored).
+// Only tiles on or below the diagonal are touched (they are the only ones stored).  Each 8x8 result tile
+// is a run of DMMA pairs over its non-zero contraction tiles; the operand addresses advance by constant
+// (A) or linearly growing (B, packed rows) strides, so the inner loop is two shared loads, two DMMAs and
+// two pointer updates.  Tile (ta, tb) costs 2(TB - tb) DMMAs in phase 1 and 2(ta + 1) in phase 2, so tiles
+// are handed out in balanced pairs {(a, b), (TB-1-a, TB-1-b)} and {(a, TB-1-b), (TB-1-a, b)}.
 template <int S, int P2_WARPS>
 __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
   constexpr int TB = S / 8;                 // 8x8 tiles per block edge
   constexpr int TILES = (NB / (2 * S)) * TB * TB;
   constexpr int PER_WARP = (TILES + P2_WARPS - 1) / P2_WARPS;
+  static_assert((TB * TB) % PER_WARP == 0, "a warp's tiles must belong to one pair of blocks");
   const int g = lane >> 2, q = lane & 3;
+  const int sw = ((g >> 1) & 1) << 2;
+  const int a_in = g * 8 + (q ^ sw);                              // A fragment: row g, col q
+  const int a4 = ((q ^ sw) ^ 4) - (q ^ sw);                       // ... col q + 4
+  const int b_in = q * 8 + (g ^ (((q >> 1) & 1) << 2));           // B fragment: row q, col g; row q + 4 is +32
+  const int c_in = g * 8 + ((2 * q) ^ sw);                        // C fragment: row g, cols 2q, 2q+1
   double c0[PER_WARP], c1[PER_WARP];
-  int ta[PER_WARP], tb[PER_WARP], t1[PER_WARP];   // tile row / column inside the pair, first tile of the pair
-  bool ok[PER_WARP];
+  int ta[PER_WARP], tb[PER_WARP];
+  const int tw = warp * PER_WARP;
+  const bool active = tw < TILES;
+  const int t1 = (active ? tw / (TB * TB) : 0) * 2 * TB;          // first tile row/column of this warp's pair
 #pragma unroll
   for (int e = 0; e < PER_WARP; e++) {
-    // Tile (ta, tb) costs 2(TB - tb) DMMAs in phase 1 and 2(ta + 1) in phase 2, so tiles are handed out in
-    // balanced pairs {(a, b), (TB-1-a, TB-1-b)} and {(a, TB-1-b), (TB-1-a, b)}: every warp gets the same work.
-    const int t = warp * PER_WARP + e;
-    ok[e] = t < TILES;
-    const int tt = ok[e] ? t : 0;
-    const int pair = tt / (TB * TB), u = tt % (TB * TB);
+    const int u = (tw + e) % (TB * TB);
     if (TB >= 2) {
       constexpr int H = TB >= 2 ? TB / 2 : 1;
       const int quad = u >> 2, m = u & 3, a = quad / H, b = quad % H;
@@ -156,50 +162,52 @@ __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
     } else {
       ta[e] = 0; tb[e] = 0;
     }
-    t1[e] = pair * 2 * TB;
-    c0[e] = c1[e] = 0.0;
   }
-  const int a_in = g * 8 + (q ^ (((g >> 1) & 1) << 2));          // A fragment: row g, col q (+ k0 & 4 below)
-  // phase 1: T = L21 * X11   (X11 lower: contraction tiles kt >= b)
-  for (int k0 = 0; k0 < S; k0 += 4) {
-    const int kt = k0 >> 3, kq = (k0 & 4) + q;                   // contraction tile, row/col inside it
-    const int b_in = kq * 8 + (g ^ (((kq >> 1) & 1) << 2));      // B fragment: row kq, col g
+  // phase 1: T = L21 * X11   (X11 lower: contraction tiles kt >= tb)
+  if (active) {
 #pragma unroll
     for (int e = 0; e < PER_WARP; e++) {
-      if (ok[e] && kt >= tb[e]) {
-        const double af = sm[tile_base(t1[e] + TB + ta[e], t1[e] + kt) + (a_in ^ (k0 & 4))];
-        const double bf = sm[tile_base(t1[e] + kt, t1[e] + tb[e]) + b_in];
-        dmma(c0[e], c1[e], af, bf);
+      const double* pa = sm + tile_base(t1 + TB + ta[e], t1 + tb[e]) + a_in;
+      const double* pb = sm + tile_base(t1 + tb[e], t1 + tb[e]) + b_in;
+      double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+      for (int kt = tb[e]; kt < TB; kt++) {
+        dmma(x0, x1, pa[0], pb[0]);
+        dmma(y0, y1, pa[a4], pb[32]);
+        pa += 64;
+        pb += (t1 + kt + 1) * 64;
       }
+      c0[e] = x0 + y0; c1[e] = x1 + y1;
     }
   }
   __syncthreads();
-  const int c_in = g * 8 + ((2 * q) ^ (((g >> 1) & 1) << 2));    // C fragment: row g, cols 2q, 2q+1
+  if (active) {
 #pragma unroll
-  for (int e = 0; e < PER_WARP; e++) {
-    if (ok[e])
-      *reinterpret_cast<double2*>(sm + tile_base(t1[e] + TB + ta[e], t1[e] + tb[e]) + c_in) = make_double2(c0[e], c1[e]);
-    c0[e] = c1[e] = 0.0;
+    for (int e = 0; e < PER_WARP; e++)
+      *reinterpret_cast<double2*>(sm + tile_base(t1 + TB + ta[e], t1 + tb[e]) + c_in) = make_double2(c0[e], c1[e]);
   }
   __syncthreads();
-  // phase 2: X21 = -X22 * T   (X22 lower: contraction tiles kt <= a)
-  for (int k0 = 0; k0 < S; k0 += 4) {
-    const int kt = k0 >> 3, kq = (k0 & 4) + q;
-    const int b_in = kq * 8 + (g ^ (((kq >> 1) & 1) << 2));
+  // phase 2: X21 = -X22 * T   (X22 lower: contraction tiles kt <= ta)
+  if (active) {
 #pragma unroll
     for (int e = 0; e < PER_WARP; e++) {
-      if (ok[e] && kt <= ta[e]) {
-        const double af = -sm[tile_base(t1[e] + TB + ta[e], t1[e] + TB + kt) + (a_in ^ (k0 & 4))];
-        const double bf = sm[tile_base(t1[e] + TB + kt, t1[e] + tb[e]) + b_in];
-        dmma(c0[e], c1[e], af, bf);
+      const double* pa = sm + tile_base(t1 + TB + ta[e], t1 + TB) + a_in;
+      const double* pb = sm + tile_base(t1 + TB, t1 + tb[e]) + b_in;
+      double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+      for (int kt = 0; kt <= ta[e]; kt++) {
+        dmma(x0, x1, pa[0], pb[0]);
+        dmma(y0, y1, pa[a4], pb[32]);
+        pa += 64;
+        pb += (t1 + TB + kt + 1) * 64;
       }
+      c0[e] = -(x0 + y0); c1[e] = -(x1 + y1);
     }
   }
   __syncthreads();
+  if (active) {
 #pragma unroll
-  for (int e = 0; e < PER_WARP; e++)
-    if (ok[e])
-      *reinterpret_cast<double2*>(sm + tile_base(t1[e] + TB + ta[e], t1[e] + tb[e]) + c_in) = make_double2(c0[e], c1[e]);
+    for (int e = 0; e < PER_WARP; e++)
+      *reinterpret_cast<double2*>(sm + tile_base(t1 + TB + ta[e], t1 + tb[e]) + c_in) = make_double2(c0[e], c1[e]);
+  }
   __syncthreads();
 }
 
@@ -228,7 +236,8 @@ __device__ long long g_p2_marks[64];
 template <int P2_THREADS>
 __global__ void __launch_bounds__(P2_THREADS, P2_THREADS == 256 ? 3 : 1)
 potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, double* __restrict__ invD,
-                 int* __restrict__ info, long long batch_k, long long batch_inv) {
+                 int* __restrict__ info, long long batch_k, long long batch_inv,
+                 const double* __restrict__ rhs_r, double* __restrict__ rhs_z, int R, long long batch_rhs_rows) {
   extern __shared__ __align__(16) double sm[];
   double* l8 = sm + PACKED;            // [36] current 8x8 factor (packed lower)
   double* rd = l8 + 64;                // [128] reciprocals of the diagonal of L
@@ -406,7 +415,42 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
   P2_MARK(54)
   inv_level_dmma<64, P2_WARPS>(sm, warp, lane);
   P2_MARK(55)
-
+  // fused forward substitution (batched fits): z_k = inv(L_kk) r_k on DMMA tiles, four right-hand sides at a
+  // time (staged in shared memory as the B operand, zero-padded to the 8 columns of a tile).  A warp owns the
+  // row tiles {w, 15 - w} (8 warps: 17 contraction tiles each) or {w} (16 warps).
+  if (rhs_r != nullptr) {
+    double* rs = rd + NB;                // [128][4]
+    const double* rk = rhs_r + (blockIdx.x * batch_rhs_rows + r0) * R;
+    double* zk = rhs_z + (blockIdx.x * batch_rhs_rows + r0) * R;
+    for (int rc = 0; rc < R; rc += 4) {
+      const int nc = min(4, R - rc);
+      for (int idx = tid; idx < NB * 4; idx += P2_THREADS) {
+        const int c = idx >> 2, j = idx & 3;
+        rs[idx] = (c < nv && j < nc) ? rk[c * R + rc + j] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int hh = 0; hh < 16 / P2_WARPS; hh++) {
+        const int ti = hh == 0 ? warp : 15 - warp;
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+        for (int kt = 0; kt <= ti; kt++) {
+          const double* ap = sm + tile_base(ti, kt) + x_in;
+          const double b0 = g < 4 ? rs[(kt * 8 + q) * 4 + g] : 0.0;
+          const double b1 = g < 4 ? rs[(kt * 8 + q + 4) * 4 + g] : 0.0;
+          dmma(c0, c1, ap[0], b0);
+          dmma(d0, d1, ap[x4], b1);
+        }
+        c0 += d0; c1 += d1;
+        const int row = ti * 8 + g;
+        if (row < nv) {
+          if (2 * q < nc) zk[row * R + rc + 2 * q] = c0;
+          if (2 * q + 1 < nc) zk[row * R + rc + 2 * q + 1] = c1;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  P2_MARK(57)
   for (int u0 = 0; u0 < NB * NB / 2 / P2_THREADS; u0 += 16) {
 #pragma unroll
     for (int u = 0; u < 16; u++) {
@@ -424,7 +468,8 @@ __global__ void zero_info_kernel(int* info, int n) {
 }
 
 int launch_potf2(double* K, long long ldk, long long N, int kblk, double* invD, int* info, int batch,
-                 long long batch_k, long long batch_inv, cudaStream_t stream) {
+                 long long batch_k, long long batch_inv, cudaStream_t stream, const double* rhs_r = nullptr,
+                 double* rhs_z = nullptr, int R = 0, long long batch_rhs_rows = 0) {
   static bool attr_set = false;
   if (!attr_set) {
     GPM_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
@@ -434,9 +479,9 @@ int launch_potf2(double* K, long long ldk, long long N, int kblk, double* invD, 
   }
   // a lone block is latency-critical (16 warps); batches are throughput-bound (8 warps, two CTAs per SM)
   if (batch >= 64)
-    potf2_inv_kernel<256><<<batch, 256, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv);
+    potf2_inv_kernel<256><<<batch, 256, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv, rhs_r, rhs_z, R, batch_rhs_rows);
   else
-    potf2_inv_kernel<512><<<batch, 512, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv);
+    potf2_inv_kernel<512><<<batch, 512, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv, rhs_r, rhs_z, R, batch_rhs_rows);
   GPM_LAUNCH_CHECK();
   return 0;
 }
@@ -460,8 +505,11 @@ static int ensure_events(gpm_handle_impl* h, int n) {
 
 // Factor `batch` matrices stacked along the rows of K (batch_rows rows apart; batch = 1 for the
 // single-matrix case).  invD: batch x nblk x NB x NB.
+// Optional fused forward substitution: rhs_r (N x R per matrix, batch_rhs_rows rows apart) enters holding the
+// right-hand side Y and is consumed as the running residual; rhs_z receives z = L^{-1} Y block by block.
 int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, double* invD, int* info,
-                  int batch, long long batch_rows, cudaStream_t s0) {
+                  int batch, long long batch_rows, cudaStream_t s0, double* rhs_r, double* rhs_z, int R,
+                  long long batch_rhs_rows) {
   const int nblk = (int)((N + NB - 1) / NB);
   const long long total_rows = (batch - 1) * batch_rows + N;
   CUtensorMap mapK, mapInv;
@@ -479,7 +527,7 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
   if (rc) return rc;
 
   auto panel = [&](int k, cudaStream_t st) -> int {
-    int r = launch_potf2(K, ldk, N, k, invD, info, batch, batch_k, batch_inv, st);
+    int r = launch_potf2(K, ldk, N, k, invD, info, batch, batch_k, batch_inv, st, rhs_r, rhs_z, R, batch_rhs_rows);
     if (r) return r;
     const int t = nblk - k - 1;   // row blocks below the diagonal
     if (t <= 0) return 0;
@@ -493,6 +541,11 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
     a.c_rows_end = N; a.c_cols_end = (long long)(k + 1) * NB;
     a.epi = EPI_STORE;
     a.tri_b = 1;                                   // inv(L_kk) is lower triangular
+    if (rhs_r) {
+      a.rhs_r = rhs_r; a.rhs_z = rhs_z; a.rhs_R = R;
+      a.rhs_z_row0 = (long long)k * NB; a.rhs_r_row0 = (long long)(k + 1) * NB;
+      a.rhs_rows_end = N; a.batch_rhs_rows = batch_rhs_rows;
+    }
     a.batch_a_rows = batch_rows; a.batch_b_rows = (long long)nblk * NB; a.batch_c_rows = batch_rows;
     return launch_gemm(h, mapK, mapInv, mapK, a, batch, st);
   };
@@ -607,5 +660,5 @@ extern "C" int gpm_potrf(gpm_handle_t handle, double* K, int64_t N, int64_t ldk,
   GPM_ARG(ws != nullptr && ((uintptr_t)ws & 15) == 0, 5);
   GPM_ARG(info != nullptr, 6);
   gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
-  return potrf_blocked(h, K, N, ldk, reinterpret_cast<double*>(ws), info, 1, 0, (cudaStream_t)stream);
+  return potrf_blocked(h, K, N, ldk, reinterpret_cast<double*>(ws), info, 1, 0, (cudaStream_t)stream, nullptr, nullptr, 0, 0);
 }

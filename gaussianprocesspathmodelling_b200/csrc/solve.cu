@@ -354,12 +354,14 @@ int solve_chain(gpm_handle_impl* h, const double* L, long long N, long long ldl,
 // streamed once per direction (128 KB in flight per CTA).  No inter-CTA dependencies.
 // ------------------------------------------------------------------------------------------------
 constexpr int SB_MAXN = 2048;
+bool solve_paths_supported(long long N) { return (N + NB - 1) / NB * NB <= SB_MAXN; }
 
 template <int RR>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 solve_path_kernel(const double* __restrict__ Lb, long long ldl, long long N, const double* __restrict__ invDb,
                   const double* __restrict__ Yb, double* __restrict__ alphab, double* __restrict__ lmlb,
-                  int R, int nblk, long long batch_l, long long batch_inv, long long batch_y) {
+                  int R, int nblk, long long batch_l, long long batch_inv, long long batch_y,
+                  const double* __restrict__ zfwd) {
   extern __shared__ double psm[];
   double* zs = psm;                                   // [nblk*128][RR]
   double* part = zs + (long long)nblk * NB * RR;      // [4][128][RR]
@@ -371,15 +373,17 @@ solve_path_kernel(const double* __restrict__ Lb, long long ldl, long long N, con
   double* alpha = alphab + blockIdx.x * batch_y;
   const int tid = threadIdx.x, e = tid & 127, qd = tid >> 7, warp = tid >> 5, lane = tid & 31;
 
+  // zfwd != nullptr: the forward substitution was fused into the factorisation; start from z = L^{-1} Y
+  const double* Z0 = zfwd ? zfwd + blockIdx.x * batch_y : Y;
   for (int idx = tid; idx < nblk * NB * RR; idx += CH_THREADS) {
     const int row = idx / RR, r = idx % RR;
-    zs[idx] = (row < N && r < R) ? Y[(long long)row * R + r] : 0.0;
+    zs[idx] = (row < N && r < R) ? Z0[(long long)row * R + r] : 0.0;
   }
   double logdet = 0.0;
   for (long long i = tid; i < N; i += CH_THREADS) logdet += log(L[i * ldl + i]);
   __syncthreads();
 
-  for (int dir = 0; dir < 2; dir++) {
+  for (int dir = zfwd ? 1 : 0; dir < 2; dir++) {
     for (int it = 0; it < nblk; it++) {
       const int i = dir ? nblk - 1 - it : it;
       const long long i0 = (long long)i * NB;
@@ -486,14 +490,14 @@ solve_path_kernel(const double* __restrict__ Lb, long long ldl, long long N, con
 // returns -1 when the shape is not supported by the one-CTA-per-path kernel
 int solve_paths(const double* L, long long N, long long ldl, const double* invD, const double* Y,
                 double* alpha, double* lml, int R, int batch, long long batch_l, long long batch_inv,
-                long long batch_y, cudaStream_t stream) {
+                long long batch_y, cudaStream_t stream, const double* zfwd) {
   const int nblk = (int)((N + NB - 1) / NB);
   if ((long long)nblk * NB > SB_MAXN) return -1;
   const int RR = R <= 1 ? 1 : (R <= 2 ? 2 : (R <= 4 ? 4 : 8));
   const int smem = (nblk * NB * RR + 4 * NB * RR + NB * RR) * 8;
   auto kern = RR == 1 ? solve_path_kernel<1> : (RR == 2 ? solve_path_kernel<2> : (RR == 4 ? solve_path_kernel<4> : solve_path_kernel<8>));
   GPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<batch, CH_THREADS, smem, stream>>>(L, ldl, N, invD, Y, alpha, lml, R, nblk, batch_l, batch_inv, batch_y);
+  kern<<<batch, CH_THREADS, smem, stream>>>(L, ldl, N, invD, Y, alpha, lml, R, nblk, batch_l, batch_inv, batch_y, zfwd);
   GPM_LAUNCH_CHECK();
   return 0;
 }

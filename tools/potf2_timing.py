@@ -22,6 +22,6 @@ fw = np.array([m[3 + 3 * p] - m[2 + 3 * p] for p in range(16)])
 up = np.array([m[4 + 3 * p] - m[3 + 3 * p] for p in range(15)])
 print("fwdsub  per panel:", fw.astype(int).tolist(), "sum", int(fw.sum()))
 print("update+lookahead factor per panel:", up.astype(int).tolist(), "sum", int(up.sum()))
-print("write L %.0f | inv level0 %.0f | levels 8/16/32/64: %.0f %.0f %.0f %.0f | store inv %.0f" % (
-    m[50] - m[48], m[51] - m[50], m[52] - m[51], m[53] - m[52], m[54] - m[53], m[55] - m[54], m[56] - m[55]))
+print("write L %.0f | inv level0 %.0f | levels 8/16/32/64: %.0f %.0f %.0f %.0f | fused z %.0f | store inv %.0f" % (
+    m[50] - m[48], m[51] - m[50], m[52] - m[51], m[53] - m[52], m[54] - m[53], m[55] - m[54], m[57] - m[55], m[56] - m[57]))
 print("total from end of load to end: %.0f cycles" % (m[56] - m[0]))
