@@ -192,6 +192,23 @@ def test_batched_golden_and_oracle(golden):
     one = GPmap.fit_gp(Xb[2], Yb[2], theta=th)
     assert nrm(alpha[2].cpu().numpy(), one.alpha.cpu().numpy()) < 1e-12
 
+def test_batched_fused_forward_matches_separate_solve(monkeypatch):
+    """The forward substitution fused into the factorisation (default for N <= 2048) against the
+    solve kernel running both passes (GPM_NO_FUSED_FWD), for odd / full right-hand-side counts."""
+    for (B, N, D, R) in ((5, 300, 2, 3), (3, 130, 3, 1), (2, 512, 2, 8)):
+        Xb, Yb, th = wl.batched_paths(B, N, seed=4, D=D, R=2)
+        rng = np.random.default_rng(R)
+        Yb = np.ascontiguousarray(np.concatenate([Yb, Yb.std() * rng.standard_normal((B, N, 6))], axis=2)[:, :, :R])
+        monkeypatch.delenv("GPM_NO_FUSED_FWD", raising=False)
+        a1, l1 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+        monkeypatch.setenv("GPM_NO_FUSED_FWD", "1")
+        a0, l0 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+        a_o, l_o = gp_ref.fit_batched(Xb, Yb, th)
+        assert nrm(a1.cpu().numpy(), a0.cpu().numpy()) < 1e-12
+        assert nrm(a1.cpu().numpy(), a_o) < MEAN_TOL
+        assert np.abs(l1.cpu().numpy() - l_o).max() < LML_TOL * np.abs(l_o).max()
+        assert np.abs(l1.cpu().numpy() - l0.cpu().numpy()).max() < 1e-12 * np.abs(l_o).max()
+
 
 def test_lml_sweep_vs_oracle():
     X, Y, _ = wl.single_path(180, seed=5, D=2, R=2)
