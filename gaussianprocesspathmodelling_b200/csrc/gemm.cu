@@ -84,8 +84,8 @@ __device__ __forceinline__ OpDesc make_op(const GemmArgs& p, const TileCoord& tc
 }
 
 #ifdef GPM_GEMM_TIMING
-__device__ long long g_gemm_marks[8 * 16];
-#define GM_MARK(slot) if (DG && p.rhs_r != nullptr && blockIdx.y == 7 && lane == 0 && (warp == 0 || warp == 7)) g_gemm_marks[(warp ? 64 : 0) + (t - t_begin) * 16 + (slot)] = clock64();
+__device__ long long g_gemm_marks[8 * 2 * 4 * 8];   // [launch % 8][warp 0 / 7][tile of the CTA][slot]
+#define GM_MARK(slot) if (DG && blockIdx.y == 7 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7) && t - t_begin < 4) g_gemm_marks[((p.dbg_launch * 2 + (warp ? 1 : 0)) * 4 + (t - t_begin)) * 8 + (slot)] = clock64();
 #else
 #define GM_MARK(slot)
 #endif
@@ -131,6 +131,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   double* red = reinterpret_cast<double*>(gen + STAGES * 2 * SLAB_BYTES);  // aliases cbuf (EPI_STORE only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef GPM_GEMM_TIMING
+  const long long t_entry = clock64();
+#endif
   const int total = p.tri ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
   // tiles of this CTA: a run of consecutive tiles, or (triangular sweep) the pair (b, tiles_m-1-b), which
   // balances the quadratically decreasing work of the row blocks
@@ -249,6 +252,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
       GM_MARK(0)
+#ifdef GPM_GEMM_TIMING
+      if (DG && blockIdx.y == 7 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7) && t == t_begin)
+        g_gemm_marks[((p.dbg_launch * 2 + (warp ? 1 : 0)) * 4) * 8 + 7] = t_entry;
+#endif
 
       for (int s = 0; s < d.nslab; s++, sg++) {
         const int st = sg % STAGES;
@@ -272,6 +279,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const long long ccol_base = d.c_col + wn * 32 + 2 * q;
       if (sub) {
         mbar_wait(bar_cfull, ct & 1);
+        GM_MARK(6)
 #pragma unroll
         for (int mt = 0; mt < 8; mt++) {
           const int r = wm * 64 + mt * 8 + g;
@@ -405,12 +413,17 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 #ifdef GPM_GEMM_TIMING
+int g_dbg_launch = 0;
 extern "C" int gpm_debug_gemm_marks(long long* out) {
-  return (int)cudaMemcpyFromSymbol(out, g_gemm_marks, sizeof(long long) * 128);
+  g_dbg_launch = 0;
+  return (int)cudaMemcpyFromSymbol(out, g_gemm_marks, sizeof(long long) * 512);
 }
 #endif
 }  // namespace gpm
 namespace gpm {
+#ifdef GPM_GEMM_TIMING
+extern int g_dbg_launch;
+#endif
 
 int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& mapB,
                 const CUtensorMap& mapC, const GemmArgs& args_in, int batch, cudaStream_t stream,
@@ -452,6 +465,9 @@ int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& 
   }
   if (args.sweep_tri || args.kstart_mode || args.kend_mode) best_c = 1;   // tiles differ in work: let the hardware balance them
   args.tiles_per_cta = best_c;
+#ifdef GPM_GEMM_TIMING
+  if (args.diag_lower || args.rhs_r) args.dbg_launch = (g_dbg_launch++) % 8;
+#endif
   dim3 grid(args.sweep_tri ? (total + 1) / 2 : (total + best_c - 1) / best_c, batch);
   if (args.diag_lower || args.rhs_r)
     gemm_nt_kernel<true><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(mapA, mapB, mapC, mapB2 ? *mapB2 : mapB, args);

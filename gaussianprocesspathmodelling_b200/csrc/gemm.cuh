@@ -51,6 +51,9 @@ struct GemmArgs {
   long long rhs_r_row0;   // first row of the residual block of tile ti = 0
   long long rhs_rows_end; // rows per matrix (exclusive bound for the residual rows)
   long long batch_rhs_rows;
+#ifdef GPM_GEMM_TIMING
+  int dbg_launch;         // instrumentation builds: slot of this launch in the phase-stamp table
+#endif
   int diag_lower;         // tile mode: tiles with ti == tj are symmetric (SYRK) and only their lower triangle is
                           // needed: the 8x8 sub-tiles strictly above the diagonal are not computed
 };

@@ -500,3 +500,42 @@ def test_run_to_run_determinism():
         else:
             assert all(torch.equal(a, b) for a, b in zip(ref[:4], cur[:4]))
             assert np.array_equal(ref[4], cur[4])
+
+
+def test_config3_size_sampled_against_oracle():
+    # 4096 paths x N=512 (BASELINE config 3): every path factors (info = 0, finite LML), a strided sample of
+    # paths matches the oracle, K alpha = Y holds for the sample, and the batch is invariant to where a path sits
+    # in it (path b of the full batch == the same path fitted in a batch of 3).
+    Xb, Yb, th = wl.batched_paths(4096, 512, seed=3, D=3, R=2)
+    alpha, lml = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+    assert bool(torch.isfinite(lml).all()) and bool(torch.isfinite(alpha).all())
+    idx = [0, 1, 777, 2048, 4095]
+    a_o, l_o = gp_ref.fit_batched(Xb[idx], Yb[idx], th)
+    assert nrm(alpha[idx].cpu().numpy(), a_o) < MEAN_TOL
+    assert np.abs(lml[idx].cpu().numpy() - l_o).max() < LML_TOL * np.abs(l_o).max()
+    for b in idx:
+        K = gp_ref.cov(Xb[b], th)
+        assert np.abs(K @ alpha[b].cpu().numpy() - Yb[b]).max() < 1e-9
+    sub = [777, 4095, 0]
+    a3, l3 = GPmap.fit_gp_batched(Xb[sub], Yb[sub], theta=th)
+    # (small batches run the 16-warp diagonal-block kernel, large ones the 8-warp one: same maths, other summation order)
+    assert nrm(a3.cpu().numpy(), alpha[sub].cpu().numpy()) < 1e-11
+    assert np.abs((l3 - lml[sub]).cpu().numpy()).max() < 1e-12 * np.abs(l_o).max()
+
+
+def test_config5_size_grid_slice_against_oracle():
+    # N=16384 model (BASELINE config 5), one 2048-point slice of the 2048x2048 grid: the variance sweep at 128 block
+    # columns against the oracle's triangular solve, and the sharded slice equals the same points of a wider slice.
+    X, Y, th = wl.single_path(16384, seed=5, D=2, R=2)
+    m = GPmap.fit_gp(X, Y, theta=th)
+    mo = gp_ref.fit(X, Y, th)
+    assert np.abs(m.lml - mo["lml"]).max() < LML_TOL * np.abs(mo["lml"]).max()
+    lo = 1000 * 2048 + 512
+    mu, var = m.predict_grid(wl.BOX, (2048, 2048), points=(lo, lo + 2048))
+    P = gp_ref.grid_points(wl.BOX, (2048, 2048))[lo:lo + 2048]
+    mu_o, var_o = gp_ref.predict(mo, P)
+    assert nrm(mu.cpu().numpy(), mu_o) < MEAN_TOL
+    assert nrm(var.cpu().numpy(), var_o) < VAR_TOL
+    assert float(var.min()) > -1e-9 and float(var.max()) <= th[2] + 1e-12
+    mu2, var2 = m.predict_grid(wl.BOX, (2048, 2048), points=(lo - 300, lo + 2048))
+    assert torch.equal(mu2[300:], mu) and torch.allclose(var2[300:], var, rtol=0, atol=1e-13)
