@@ -2,6 +2,8 @@
 // off-diagonal 64x64 tile is evaluated once and stored twice, direct and transposed, both
 // coalesced), the materialised query-major cross-covariance, and the fused posterior mean.
 // CUDA cores only: the input dimension is 2-3, there is no contraction to give a tensor core.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gpm {
@@ -227,6 +229,151 @@ predict_mean_kernel(const double* __restrict__ X, long long N, Theta th, const d
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Regular-grid queries: the RBF kernel is separable,
+//     k((x_a, y_b), p_i) = [exp(-(x_a - p_ix)^2 / 2)] * [sf2 exp(-((y_b - p_iy)^2 [+ (t - p_it)^2]) / 2)]
+// (coordinates pre-scaled by the lengthscales), so a PA x PB patch of grid points needs PA + PB exponentials
+// per training point instead of PA * PB.  The two kernels below evaluate the factors on the fly per patch (no
+// tables in HBM): the materialised cross-covariance becomes a pure HBM-write stream and the mean an FMA loop.
+// A query's value does not depend on which patch or launch it falls into (bitwise), so sharded ranges
+// concatenate exactly.  The product of two correctly rounded factors differs from the single exponential of
+// the oracle by at most ~2 ulp.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ double grid_x(const gpm_grid_t& g, long long ix) {
+  const double sx = g.gx > 1 ? (g.x1 - g.x0) / (double)(g.gx - 1) : 0.0;
+  return (ix == g.gx - 1 && g.gx > 1) ? g.x1 : __dadd_rn(__dmul_rn((double)ix, sx), g.x0);
+}
+__device__ __forceinline__ double grid_y(const gpm_grid_t& g, long long iy) {
+  const double sy = g.gy > 1 ? (g.y1 - g.y0) / (double)(g.gy - 1) : 0.0;
+  return (iy == g.gy - 1 && g.gy > 1) ? g.y1 : __dadd_rn(__dmul_rn((double)iy, sy), g.y0);
+}
+
+// KsT[m - m0, i] for the grid points m in [m0, m0 + M): a CTA owns a patch of 8 grid columns x 8 grid rows and a
+// run of `cols_per_cta` training columns, one column per thread and step; every store instruction of a warp
+// writes 256 contiguous bytes of one row.  Columns [N, ncols_pad) are zeroed.
+template <int D>
+__global__ void __launch_bounds__(256, 3)
+cross_cov_grid_kernel(const double* __restrict__ X, long long N, Theta th, gpm_grid_t grid, long long m0,
+                      long long M, long long row_first, double* __restrict__ KsT, long long ldks,
+                      long long ncols_pad, int cols_per_cta) {
+  constexpr int PA = 8, PB = 8;
+  __shared__ double sqy[PB];
+  const int a0 = blockIdx.x * PA;
+  const long long b0 = row_first + (long long)blockIdx.y * PB;
+  if (threadIdx.x < PB) sqy[threadIdx.x] = grid_y(grid, b0 + threadIdx.x) / th.l[1];
+  double qx[PA];
+#pragma unroll
+  for (int r = 0; r < PA; r++) qx[r] = grid_x(grid, a0 + r) / th.l[0];
+  const double qt = D == 3 ? grid.t / th.l[2] : 0.0;
+  // which of the 64 patch points lie inside [m0, m0 + M) and inside the grid row
+  unsigned long long mask = 0;
+#pragma unroll
+  for (int rb = 0; rb < PB; rb++)
+#pragma unroll
+    for (int ra = 0; ra < PA; ra++) {
+      const long long m = (b0 + rb) * grid.gx + a0 + ra;
+      if (a0 + ra < grid.gx && m >= m0 && m < m0 + M) mask |= 1ull << (rb * PA + ra);
+    }
+  __syncthreads();
+  if (mask == 0) return;
+  const long long c_begin = (long long)blockIdx.z * cols_per_cta;
+  const long long c_end = min(ncols_pad, c_begin + cols_per_cta);
+  double* const row0 = KsT + (b0 * grid.gx + a0 - m0) * ldks;      // patch point (0, 0); only masked-in rows are touched
+  const long long row_pitch = (long long)grid.gx * ldks;            // one grid row further
+  for (long long i = c_begin + threadIdx.x; i < c_end; i += 256) {
+    const bool in = i < N;
+    double ex[PA], py = 0.0, dt2 = 0.0;
+    if (in) {
+      const double px = X[i * D] / th.l[0];
+      py = X[i * D + 1] / th.l[1];
+      if (D == 3) { const double dt = qt - X[i * D + 2] / th.l[2]; dt2 = __dmul_rn(dt, dt); }
+#pragma unroll
+      for (int r = 0; r < PA; r++) { const double dx = qx[r] - px; ex[r] = exp(-0.5 * __dmul_rn(dx, dx)); }
+    } else {
+#pragma unroll
+      for (int r = 0; r < PA; r++) ex[r] = 0.0;
+    }
+    double* prow = row0 + i;
+#pragma unroll 1
+    for (int rb = 0; rb < PB; rb++, prow += row_pitch) {
+      const unsigned rm = (unsigned)(mask >> (rb * PA)) & 0xffu;
+      if (rm == 0) continue;
+      const double dy = sqy[rb] - py;
+      const double d2 = D == 3 ? __dadd_rn(__dmul_rn(dy, dy), dt2) : __dmul_rn(dy, dy);
+      const double ey = in ? th.sf2 * exp(-0.5 * d2) : 0.0;
+#pragma unroll
+      for (int ra = 0; ra < PA; ra++)
+        if (rm >> ra & 1) prow[ra * ldks] = ex[ra] * ey;
+    }
+  }
+}
+
+// mu[m - m0, r] = sum_i k(grid point m, x_i) alpha[i, r] for m in [m0, m0 + M): a CTA owns a patch of 16 x 16 grid
+// points (one per thread); per chunk of 128 training points the 2 x 16 x 128 factors are evaluated once into shared
+// memory (16 exponentials per thread) and every thread runs a load-load-multiply-FMA loop over the chunk.
+template <int D, int RR>
+__global__ void __launch_bounds__(256)
+predict_mean_grid_kernel(const double* __restrict__ X, long long N, Theta th, const double* __restrict__ alpha,
+                         int R, gpm_grid_t grid, long long m0, long long M, long long row_first,
+                         double* __restrict__ mu) {
+  constexpr int PA = 16, PB = 16, CH = 128;
+  __shared__ double exs[CH][PA], eys[CH][PB], sa[CH][RR], sx[CH][3], sq[2][16];
+  const int tid = threadIdx.x, ta = tid & 15, tb = tid >> 4;
+  const int a0 = blockIdx.x * PA;
+  const long long b0 = row_first + (long long)blockIdx.y * PB;
+  if (tid < 16) sq[0][tid] = grid_x(grid, a0 + tid) / th.l[0];
+  else if (tid < 32) sq[1][tid - 16] = grid_y(grid, b0 + tid - 16) / th.l[1];
+  const double qt = D == 3 ? grid.t / th.l[2] : 0.0;
+  double acc[RR];
+#pragma unroll
+  for (int r = 0; r < RR; r++) acc[r] = 0.0;
+  for (long long i0 = 0; i0 < N; i0 += CH) {
+    const int n = (int)((N - i0) < CH ? (N - i0) : CH);
+    __syncthreads();                       // previous chunk consumed (and sq written, first time round)
+    for (int e = tid; e < n * D; e += 256) {
+      const int c = e / D, d = e % D;
+      sx[c][d] = X[(i0 + c) * D + d] / (d == 0 ? th.l[0] : (d == 1 ? th.l[1] : th.l[2]));
+    }
+    for (int e = tid; e < n * RR; e += 256) { const int c = e / RR, k = e % RR; sa[c][k] = k < R ? alpha[(i0 + c) * R + k] : 0.0; }
+    __syncthreads();
+#pragma unroll 4
+    for (int e = tid; e < 2 * CH * 16; e += 256) {
+      const int which = e / (CH * 16), c = (e / 16) % CH, r = e % 16;     // consecutive threads: consecutive r
+      if (c < n) {
+        if (which == 0) {
+          const double dx = sq[0][r] - sx[c][0];
+          exs[c][r] = exp(-0.5 * __dmul_rn(dx, dx));
+        } else {
+          const double dy = sq[1][r] - sx[c][1];
+          double d2 = __dmul_rn(dy, dy);
+          if (D == 3) { const double dt = qt - sx[c][2]; d2 = __dadd_rn(d2, __dmul_rn(dt, dt)); }
+          eys[c][r] = th.sf2 * exp(-0.5 * d2);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int i = 0; i < n; i++) {
+      const double kv = exs[i][ta] * eys[i][tb];
+#pragma unroll
+      for (int r = 0; r < RR; r++) acc[r] = fma(kv, sa[i][r], acc[r]);
+    }
+  }
+  const long long m = (b0 + tb) * grid.gx + a0 + ta;
+  if (a0 + ta < grid.gx && m >= m0 && m < m0 + M) {
+#pragma unroll
+    for (int r = 0; r < RR; r++) if (r < R) mu[(m - m0) * R + r] = acc[r];
+  }
+}
+
+// separable grid kernels are used for grid queries unless GPM_NO_SEPARABLE is set (debugging / comparison)
+bool grid_separable_enabled(const gpm_grid_t* grid, long long m0, long long M) {
+  if (!grid || M <= 0 || grid->gx <= 0 || getenv("GPM_NO_SEPARABLE") != nullptr) return false;
+  const long long rows = (m0 + M - 1) / grid->gx - m0 / grid->gx + 1;
+  return (rows + 7) / 8 <= 65535;        // gridDim.y
+}
+
 int launch_cov(const double* X, long long N, int D, const Theta& th, double* K, long long ldk,
                int lower_only, int batch, long long batch_x, long long batch_k, cudaStream_t stream,
                const double* theta_dev, int theta_stride) {
@@ -245,6 +392,15 @@ int launch_cross_cov_t(const double* X, long long N, int D, const Theta& th, con
   gpm_grid_t g = {};
   if (grid) g = *grid;
   const int use_grid = Xs == nullptr;
+  if (use_grid && grid_separable_enabled(grid, m0, M)) {
+    const long long row_first = m0 / g.gx, rows = (m0 + M - 1) / g.gx - row_first + 1;
+    const int cols_per_cta = 1024;
+    dim3 gd((unsigned)((g.gx + 7) / 8), (unsigned)((rows + 7) / 8), (unsigned)((ncols_pad + cols_per_cta - 1) / cols_per_cta));
+    if (D == 2) cross_cov_grid_kernel<2><<<gd, 256, 0, stream>>>(X, N, th, g, m0, M, row_first, KsT, ldks, ncols_pad, cols_per_cta);
+    else cross_cov_grid_kernel<3><<<gd, 256, 0, stream>>>(X, N, th, g, m0, M, row_first, KsT, ldks, ncols_pad, cols_per_cta);
+    GPM_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 gridDim((unsigned)((M + 31) / 32), (unsigned)((ncols_pad + 255) / 256));
   if (D == 2) cross_cov_t_kernel<2><<<gridDim, 256, 0, stream>>>(X, N, th, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad);
   else cross_cov_t_kernel<3><<<gridDim, 256, 0, stream>>>(X, N, th, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad);
@@ -281,6 +437,16 @@ template <int D>
 static int launch_mean_d(const double* X, long long N, const Theta& th, const double* alpha, int R,
                          const double* Xs, const gpm_grid_t& g, int use_grid, long long m0, long long M,
                          double* mu, cudaStream_t stream) {
+  if (use_grid && grid_separable_enabled(&g, m0, M)) {
+    const long long row_first = m0 / g.gx, rows = (m0 + M - 1) / g.gx - row_first + 1;
+    dim3 gd((unsigned)((g.gx + 15) / 16), (unsigned)((rows + 15) / 16));
+    if (R <= 1) predict_mean_grid_kernel<D, 1><<<gd, 256, 0, stream>>>(X, N, th, alpha, R, g, m0, M, row_first, mu);
+    else if (R <= 2) predict_mean_grid_kernel<D, 2><<<gd, 256, 0, stream>>>(X, N, th, alpha, R, g, m0, M, row_first, mu);
+    else if (R <= 4) predict_mean_grid_kernel<D, 4><<<gd, 256, 0, stream>>>(X, N, th, alpha, R, g, m0, M, row_first, mu);
+    else predict_mean_grid_kernel<D, 8><<<gd, 256, 0, stream>>>(X, N, th, alpha, R, g, m0, M, row_first, mu);
+    GPM_LAUNCH_CHECK();
+    return 0;
+  }
   const unsigned blocks = (unsigned)((M + 255) / 256);
   if (R <= 1) predict_mean_kernel<D, 1><<<blocks, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, mu);
   else if (R <= 2) predict_mean_kernel<D, 2><<<blocks, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, mu);

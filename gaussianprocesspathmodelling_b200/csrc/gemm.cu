@@ -428,11 +428,10 @@ extern int g_dbg_launch;
 int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& mapB,
                 const CUtensorMap& mapC, const GemmArgs& args_in, int batch, cudaStream_t stream,
                 const CUtensorMap* mapB2) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->gemm_attr) {
     GPM_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     GPM_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    attr_set = true;
+    h->gemm_attr = true;
   }
   GemmArgs args = args_in;
   if (args.sweep_nblk > 0) {

@@ -467,15 +467,14 @@ __global__ void zero_info_kernel(int* info, int n) {
   if (i < n) info[i] = 0;
 }
 
-int launch_potf2(double* K, long long ldk, long long N, int kblk, double* invD, int* info, int batch,
+int launch_potf2(gpm_handle_impl* h, double* K, long long ldk, long long N, int kblk, double* invD, int* info, int batch,
                  long long batch_k, long long batch_inv, cudaStream_t stream, const double* rhs_r = nullptr,
                  double* rhs_z = nullptr, int R = 0, long long batch_rhs_rows = 0) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->potf2_attr) {
     GPM_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
     GPM_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     GPM_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM));
-    attr_set = true;
+    h->potf2_attr = true;
   }
   // a lone block is latency-critical (16 warps); batches are throughput-bound (8 warps, two CTAs per SM)
   if (batch >= 64)
@@ -527,7 +526,7 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
   if (rc) return rc;
 
   auto panel = [&](int k, cudaStream_t st) -> int {
-    int r = launch_potf2(K, ldk, N, k, invD, info, batch, batch_k, batch_inv, st, rhs_r, rhs_z, R, batch_rhs_rows);
+    int r = launch_potf2(h, K, ldk, N, k, invD, info, batch, batch_k, batch_inv, st, rhs_r, rhs_z, R, batch_rhs_rows);
     if (r) return r;
     const int t = nblk - k - 1;   // row blocks below the diagonal
     if (t <= 0) return 0;

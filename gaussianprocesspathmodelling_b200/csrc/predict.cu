@@ -22,6 +22,7 @@ int launch_cross_cov_mean(const double* X, long long N, int D, const Theta& th, 
 int launch_predict_mean(const double* X, long long N, int D, const Theta& th, const double* alpha, int R,
                         const double* Xs, const gpm_grid_t* grid, long long m0, long long M, double* mu,
                         cudaStream_t stream);
+bool grid_separable_enabled(const gpm_grid_t* grid, long long m0, long long M);
 
 __global__ void var_finalize_kernel(const double* __restrict__ rowsq, long long M, double base,
                                     double* __restrict__ var) {
@@ -79,7 +80,9 @@ extern "C" int gpm_predict(gpm_handle_t handle, const double* X, int64_t N, int3
     GPM_ARG(R >= 1 && R <= 8, 10);
     GPM_ARG(mu != nullptr, 15);
     // with the variance requested and R <= 2 the mean is fused into the cross-covariance pass below
-    fuse_mean = (flags & GPM_PREDICT_VAR) && R <= 2 && getenv("GPM_NO_FUSED_MEAN") == nullptr;
+    // (grid queries: the separable mean kernel + the separable cross-covariance are cheaper than the fused pass)
+    fuse_mean = (flags & GPM_PREDICT_VAR) && R <= 2 && getenv("GPM_NO_FUSED_MEAN") == nullptr &&
+                !(Xs == nullptr && grid_separable_enabled(grid, m0, M));
     if (!fuse_mean && (rc = launch_predict_mean(X, N, D, th, alpha, R, Xs, grid, m0, M, mu, st))) return rc;
   }
   if (!(flags & GPM_PREDICT_VAR)) return 0;

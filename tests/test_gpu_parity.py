@@ -539,3 +539,34 @@ def test_config5_size_grid_slice_against_oracle():
     assert float(var.min()) > -1e-9 and float(var.max()) <= th[2] + 1e-12
     mu2, var2 = m.predict_grid(wl.BOX, (2048, 2048), points=(lo - 300, lo + 2048))
     assert torch.equal(mu2[300:], mu) and torch.allclose(var2[300:], var, rtol=0, atol=1e-13)
+
+
+def test_separable_grid_kernels_match_the_pointwise_ones(monkeypatch):
+    """Grid queries use the separable form of the RBF kernel (PA + PB exponentials per patch and training point);
+    the pointwise kernels (GPM_NO_SEPARABLE, also what predict(Xs) runs) must agree to rounding, for ragged grids,
+    D = 3 with a query time, R up to 8, and flat sub-ranges that start and end inside grid rows."""
+    for (N, D, R, G, t) in ((300, 2, 2, (37, 23), None), (257, 3, 1, (5, 70), 31.0), (140, 2, 8, (130, 9), None)):
+        X, Y, th = wl.single_path(N, seed=6, D=D, R=2)
+        rng = np.random.default_rng(N)
+        Y = np.ascontiguousarray(np.concatenate([Y, rng.standard_normal((N, 6))], axis=1)[:, :R])
+        m = GPmap.fit_gp(X, Y, theta=th)
+        M = G[0] * G[1]
+        for pts in (None, (G[0] + 3, M - 5), (7, 9)):
+            monkeypatch.delenv("GPM_NO_SEPARABLE", raising=False)
+            mu1, var1 = m.predict_grid(wl.BOX, G, t=t, points=pts)
+            mo1 = m.predict_grid(wl.BOX, G, t=t, points=pts, return_var=False)
+            monkeypatch.setenv("GPM_NO_SEPARABLE", "1")
+            mu0, var0 = m.predict_grid(wl.BOX, G, t=t, points=pts)
+            monkeypatch.delenv("GPM_NO_SEPARABLE", raising=False)
+            assert torch.equal(mo1, mu1)                                   # mean-only and mean+variance calls agree bitwise
+            assert nrm(mu1.cpu().numpy(), mu0.cpu().numpy()) < 1e-12
+            assert nrm(var1.cpu().numpy(), var0.cpu().numpy()) < 1e-11
+        # against the oracle, and against predict() on the same points given explicitly
+        P = gp_ref.grid_points(wl.BOX, G, t=t)
+        mo = gp_ref.fit(X, Y, th)
+        mu_o, var_o = gp_ref.predict(mo, P)
+        mu1, var1 = m.predict_grid(wl.BOX, G, t=t)
+        assert nrm(mu1.reshape(-1, R).cpu().numpy(), mu_o) < MEAN_TOL
+        assert nrm(var1.reshape(-1).cpu().numpy(), var_o) < VAR_TOL
+        mu2, var2 = m.predict(P)
+        assert nrm(mu1.reshape(-1, R).cpu().numpy(), mu2.cpu().numpy()) < 1e-12
