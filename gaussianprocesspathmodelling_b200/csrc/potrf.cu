@@ -249,6 +249,9 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
   const long long r0 = (long long)kblk * NB;
   const int nv = (int)((N - r0) < NB ? (N - r0) : NB);
 
+#ifdef GPM_POTF2_TIMING
+  if (tid == 0 && blockIdx.x == 0) g_p2_marks[58] = clock64();
+#endif
   // load the lower triangle as 16-byte pairs (LU independent loads in flight per thread); identity padding
   // beyond nv.  A pair never straddles a tile and keeps its order under the in-tile swizzle (bit 2 only).
   constexpr int LU = P2_THREADS == 256 ? 8 : 16;   // loads in flight per thread (register budget)

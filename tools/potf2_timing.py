@@ -17,7 +17,7 @@ torch.cuda.synchronize()
 buf = (C.c_longlong * 64)()
 lib.gpm_debug_potf2_marks(buf)
 m = np.frombuffer(buf, dtype=np.int64).astype(np.float64)
-print("first barrier %.0f, first 8x8 factor %.0f" % (m[1] - m[0], m[2] - m[1]))
+print("load %.0f, first barrier %.0f, first 8x8 factor %.0f" % (m[0] - m[58], m[1] - m[0], m[2] - m[1]))
 fw = np.array([m[3 + 3 * p] - m[2 + 3 * p] for p in range(16)])
 up = np.array([m[4 + 3 * p] - m[3 + 3 * p] for p in range(15)])
 print("fwdsub  per panel:", fw.astype(int).tolist(), "sum", int(fw.sum()))
