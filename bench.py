@@ -459,6 +459,14 @@ def run_b200(args):
         t_b = max_over_ranks(t_b)
         extra["cfg3_batched"] = {"paths_per_gpu": B, "N": 512, "ms": t_b, "fits_per_s": world * B / (t_b * 1e-3),
                                  "frac_of_fp64_ceiling": (world * B / (t_b * 1e-3)) * 5.1e7 / (world * peaks["fp64_tflops"] * 1e12)}
+        # the reference's own path length (GPmap.py:189 resamples every trajectory to 33 points): one CTA per path
+        del Xbd, Ybd
+        Bs = 16384
+        Xs_, Ys_, ths_ = wl.batched_paths(Bs, 33, seed=3, D=2, R=2, first=rank * Bs)
+        Xsd, Ysd = torch.from_numpy(Xs_).to(dev), torch.from_numpy(Ys_).to(dev)
+        t_s = max_over_ranks(timed(torch, lambda: GPmap.fit_gp_batched(Xsd, Ysd, theta=ths_, check=False), 5, warm=2))
+        extra["short_paths_N33"] = {"paths_per_gpu": Bs, "N": 33, "ms": t_s, "fits_per_s": world * Bs / (t_s * 1e-3),
+                                    "kernel": "fit_small_kernel: one CTA per path, whole fit in shared memory"}
 
     # ---- CPU baseline on this box (rank 0, N=1 only) --------------------------------------------
     cpu = None

@@ -22,6 +22,11 @@ int solve_paths(const double* L, long long N, long long ldl, const double* invD,
 int launch_lml(const double* L, long long N, long long ldl, const double* Y, const double* alpha, int R,
                double* lml, int batch, long long batch_l, long long batch_y, cudaStream_t stream);
 
+bool fit_small_supported(long long N);
+int launch_fit_small(const double* Xb, const double* Yb, long long B, long long N, int D, int R, const Theta& th,
+                     const double* theta_dev, int theta_stride, double* alpha, double* lml, int* info,
+                     cudaStream_t stream);
+
 static inline long long round_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
 
 }  // namespace gpm
@@ -30,6 +35,7 @@ using namespace gpm;
 
 extern "C" size_t gpm_fit_batched_workspace_bytes(int64_t B, int64_t N) {
   if (B <= 0 || N <= 0) return 0;
+  if (fit_small_supported(N)) return (size_t)B * 8 * sizeof(double);       // one CTA per path: only per-path theta is staged
   const long long np = round_up_ll(N, NB);
   return (size_t)B * (size_t)(np * np + np * NB + 8 + np * 8) * sizeof(double);   // + per-path theta + z = L^{-1} Y
 }
@@ -40,7 +46,7 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
   GPM_ARG(handle != nullptr, 1);
   GPM_ARG(Xb != nullptr, 2);
   GPM_ARG(Yb != nullptr, 3);
-  GPM_ARG(B > 0 && B <= 65535, 4);
+  GPM_ARG(B > 0 && (B <= 65535 || (fit_small_supported(N) && B < (1ll << 31))), 4);   // gridDim.y / gridDim.x
   GPM_ARG(N > 0 && B * ((N + NB - 1) / NB * NB) < (1ll << 31), 5);
   Theta th;
   GPM_ARG(R >= 1 && R <= 8, 7);
@@ -52,6 +58,15 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
   GPM_ARG(ws != nullptr && ((uintptr_t)ws & 15) == 0, 13);
   gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
   cudaStream_t st = (cudaStream_t)stream;
+  if (fit_small_supported(N)) {
+    // short paths (the reference's 33-sample trajectories): one CTA per path, the whole fit in shared memory
+    const double* tdev = nullptr;
+    if (theta_stride) {
+      GPM_CUDA(cudaMemcpyAsync(ws, theta, (size_t)B * (D + 2) * sizeof(double), cudaMemcpyHostToDevice, st));
+      tdev = reinterpret_cast<const double*>(ws);
+    }
+    return launch_fit_small(Xb, Yb, B, N, D, R, th, tdev, (int)theta_stride, alpha, lml, info, st);
+  }
   const long long np = round_up_ll(N, NB);
   const int nblk = (int)(np / NB);
   double* Kb = reinterpret_cast<double*>(ws);            // B stacked np x np matrices, ld = np

@@ -1,0 +1,193 @@
+// Batched fits of SHORT paths (N <= 112, the reference's regime: GPmap.py:189 resamples every trajectory to 33
+// points): ONE CTA PER PATH, the whole fit in shared memory.
+//
+//   covariance (lower triangle, packed)  ->  Cholesky (left-looking, one thread per row)  ->  forward and backward
+//   substitution  ->  alpha, log marginal likelihood
+//
+// Nothing but X, Y (in) and alpha, lml, info (out) touches HBM: 8 N (D + 2R) + 8R bytes per path, where the tiled
+// pipeline of batched.cu writes and re-reads a padded 128 x 128 block three times.  A path of N = 33 needs 4.5 KB of
+// shared memory, so 16 CTAs share an SM and hide each other's barrier and pivot latencies; N = 112 needs 52 KB.
+// Measured (B200): N=33 41.9 M fits/s (tiled pipeline 5.0 M), N=64 16.8 M, N=96 6.0 M (4.0 M).
+// FP64 CUDA cores only: a 33 x 33 factorisation is 12 kflop, less than the 561 exponentials of its covariance.
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace gpm {
+
+constexpr int SMALL_MAX_N = 112;     // measured crossover with the tiled pipeline (8192 paths: N=96 6.0 vs 4.0 M fits/s, N=112 3.8 vs 3.8, N=128 2.8 vs 3.9)
+
+__host__ __device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
+
+template <int D, int RR>
+__global__ void __launch_bounds__(128)
+fit_small_kernel(const double* __restrict__ Xb, const double* __restrict__ Yb, int N, int R, Theta th,
+                 const double* __restrict__ theta_dev, int theta_stride, double* __restrict__ alphab,
+                 double* __restrict__ lmlb, int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  double* Kp = sm;                          // packed lower triangle, row i at i(i+1)/2
+  double* xs = Kp + tri(N);                 // [N][3] coordinates / lengthscale
+  double* dinv = xs + 3 * N;                // [N] 1 / L_ii
+  double* piv = dinv + N;                   // [N] pivots d_j (broadcast from the diagonal row to the rows below)
+  double* vs = piv + N;                     // [N][RR] the solved entry of the current substitution step
+  double* red = vs + N * RR;                // [4][RR + 1] cross-warp reduction
+  const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+  const long long b = blockIdx.x;
+  if (theta_dev) {                          // per-path hyper-parameters
+    const double* t = theta_dev + b * theta_stride;
+#pragma unroll
+    for (int d = 0; d < D; d++) th.l[d] = t[d];
+    th.sf2 = t[D];
+    th.sn2 = t[D + 1];
+  }
+  const double* X = Xb + b * N * D;
+  const double* Y = Yb + b * N * R;
+  for (int e = tid; e < N * D; e += nthr) {
+    const int i = e / D, d = e % D;
+    xs[i * 3 + d] = X[e] / (d == 0 ? th.l[0] : (d == 1 ? th.l[1] : th.l[2]));
+  }
+  const int i = tid;                        // the row this thread owns
+  double y[RR], y0[RR];
+#pragma unroll
+  for (int r = 0; r < RR; r++) y0[r] = y[r] = (i < N && r < R) ? Y[i * R + r] : 0.0;
+  __syncthreads();
+
+  // ---- covariance: rows dealt to warps, columns to lanes (same arithmetic as cov_kernel) ----
+  for (int r = warp; r < N; r += nwarp) {
+    const double a[3] = {xs[r * 3], xs[r * 3 + 1], D == 3 ? xs[r * 3 + 2] : 0.0};
+    for (int c = lane; c <= r; c += 32) {
+      const double bq[3] = {xs[c * 3], xs[c * 3 + 1], D == 3 ? xs[c * 3 + 2] : 0.0};
+      double v = rbf<D>(a, bq, th.sf2);
+      if (c == r) v += th.sn2;
+      Kp[tri(r) + c] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- Cholesky, left-looking: column j of L from the finished columns 0..j-1 (two barriers per column) ----
+  int bad = 0;
+  for (int j = 0; j < N; j++) {
+    const bool act = i >= j && i < N;
+    double s = 0.0;
+    if (act) {
+      const double* ri = Kp + tri(i);
+      const double* rj = Kp + tri(j);
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int k = 0;
+      for (; k + 7 < j; k += 8) {               // sixteen independent shared loads in flight per step
+        const double a0 = ri[k], a1 = ri[k + 1], a2 = ri[k + 2], a3 = ri[k + 3];
+        const double a4 = ri[k + 4], a5 = ri[k + 5], a6 = ri[k + 6], a7 = ri[k + 7];
+        const double b0 = rj[k], b1 = rj[k + 1], b2 = rj[k + 2], b3 = rj[k + 3];
+        const double b4 = rj[k + 4], b5 = rj[k + 5], b6 = rj[k + 6], b7 = rj[k + 7];
+        s0 = fma(a0, b0, s0); s1 = fma(a1, b1, s1); s2 = fma(a2, b2, s2); s3 = fma(a3, b3, s3);
+        s0 = fma(a4, b4, s0); s1 = fma(a5, b5, s1); s2 = fma(a6, b6, s2); s3 = fma(a7, b7, s3);
+      }
+      for (; k < j; k++) s0 = fma(ri[k], rj[k], s0);
+      s = ri[j] - ((s0 + s1) + (s2 + s3));
+      if (i == j) piv[j] = s;                // the pivot d_j; the rows below keep their unnormalised entry in a register
+    }
+    __syncthreads();
+    if (act) {
+      double d = piv[j];
+      if (!(d > 0.0) || !(d < 1.0e300)) { if (!bad) bad = j + 1; d = 1.0; }
+      const double rinv = rsqrt(d);          // as potf2: 1 ulp, a fifth of the latency of sqrt + divide
+      if (i == j) { dinv[j] = rinv; Kp[tri(j) + j] = d * rinv; }
+      else Kp[tri(i) + j] = s * rinv;
+    }
+    __syncthreads();
+  }
+  if (i == N - 1) info[b] = bad;            // row N-1 takes part in every column, so it saw the first bad pivot
+
+  // ---- forward substitution L z = y (column-oriented: one barrier per step) ----
+  for (int j = 0; j < N; j++) {
+    if (i == j) {
+#pragma unroll
+      for (int r = 0; r < RR; r++) { y[r] *= dinv[j]; vs[j * RR + r] = y[r]; }
+    }
+    __syncthreads();
+    if (i > j && i < N) {
+      const double l = Kp[tri(i) + j];
+#pragma unroll
+      for (int r = 0; r < RR; r++) y[r] = fma(-l, vs[j * RR + r], y[r]);
+    }
+  }
+  __syncthreads();
+  // ---- backward substitution L^T alpha = z ----
+  for (int j = N - 1; j >= 0; j--) {
+    if (i == j) {
+#pragma unroll
+      for (int r = 0; r < RR; r++) { y[r] *= dinv[j]; vs[j * RR + r] = y[r]; }
+    }
+    __syncthreads();
+    if (i < j) {
+      const double l = Kp[tri(j) + i];
+#pragma unroll
+      for (int r = 0; r < RR; r++) y[r] = fma(-l, vs[j * RR + r], y[r]);
+    }
+  }
+  if (i < N) {
+    double* al = alphab + b * N * R + i * R;
+#pragma unroll
+    for (int r = 0; r < RR; r++) if (r < R) al[r] = y[r];
+  }
+  if (lmlb == nullptr) return;
+
+  // ---- lml[r] = -1/2 y^T alpha - sum_i log L_ii - N/2 log(2 pi); reductions in a fixed order ----
+  double part[RR + 1];
+#pragma unroll
+  for (int r = 0; r < RR; r++) part[r] = (i < N) ? y0[r] * y[r] : 0.0;
+  part[RR] = (i < N) ? log(Kp[tri(i) + i]) : 0.0;
+#pragma unroll
+  for (int r = 0; r <= RR; r++) {
+    const double sv = warp_sum(part[r]);
+    if (lane == 0) red[warp * (RR + 1) + r] = sv;
+  }
+  __syncthreads();
+  if (tid < R) {
+    double q = 0.0, ld = 0.0;
+    for (int w = 0; w < nwarp; w++) { q += red[w * (RR + 1) + tid]; ld += red[w * (RR + 1) + RR]; }
+    lmlb[b * R + tid] = -0.5 * q - ld - 0.5 * (double)N * 1.8378770664093453;   // log(2 pi)
+  }
+}
+
+bool fit_small_supported(long long N) {
+  return N >= 1 && N <= SMALL_MAX_N && getenv("GPM_NO_SMALL_FUSED") == nullptr;
+}
+
+static size_t small_smem(int N, int RR) {
+  return (size_t)(tri(N) + 3 * N + 2 * N + N * RR + 4 * (RR + 1)) * sizeof(double);
+}
+
+template <int D, int RR>
+static int launch_small_dr(const double* Xb, const double* Yb, int B, int N, int R, const Theta& th,
+                           const double* theta_dev, int theta_stride, double* alpha, double* lml, int* info,
+                           cudaStream_t stream) {
+  const size_t smem = small_smem(N, RR);
+  if (smem > 48 * 1024)
+    GPM_CUDA(cudaFuncSetAttribute(fit_small_kernel<D, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = (N + 31) / 32 * 32;
+  fit_small_kernel<D, RR><<<B, threads, smem, stream>>>(Xb, Yb, N, R, th, theta_dev, theta_stride, alpha, lml, info);
+  GPM_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int D>
+static int launch_small_d(const double* Xb, const double* Yb, int B, int N, int R, const Theta& th,
+                          const double* theta_dev, int theta_stride, double* alpha, double* lml, int* info,
+                          cudaStream_t stream) {
+  if (R <= 1) return launch_small_dr<D, 1>(Xb, Yb, B, N, R, th, theta_dev, theta_stride, alpha, lml, info, stream);
+  if (R <= 2) return launch_small_dr<D, 2>(Xb, Yb, B, N, R, th, theta_dev, theta_stride, alpha, lml, info, stream);
+  if (R <= 4) return launch_small_dr<D, 4>(Xb, Yb, B, N, R, th, theta_dev, theta_stride, alpha, lml, info, stream);
+  return launch_small_dr<D, 8>(Xb, Yb, B, N, R, th, theta_dev, theta_stride, alpha, lml, info, stream);
+}
+
+// B paths of N <= SMALL_MAX_N samples each, one CTA per path.  theta_dev: optional per-path hyper-parameters (device).
+int launch_fit_small(const double* Xb, const double* Yb, long long B, long long N, int D, int R, const Theta& th,
+                     const double* theta_dev, int theta_stride, double* alpha, double* lml, int* info,
+                     cudaStream_t stream) {
+  return D == 2 ? launch_small_d<2>(Xb, Yb, (int)B, (int)N, R, th, theta_dev, theta_stride, alpha, lml, info, stream)
+                : launch_small_d<3>(Xb, Yb, (int)B, (int)N, R, th, theta_dev, theta_stride, alpha, lml, info, stream);
+}
+
+}  // namespace gpm

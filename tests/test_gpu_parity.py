@@ -570,3 +570,41 @@ def test_separable_grid_kernels_match_the_pointwise_ones(monkeypatch):
         assert nrm(var1.reshape(-1).cpu().numpy(), var_o) < VAR_TOL
         mu2, var2 = m.predict(P)
         assert nrm(mu1.reshape(-1, R).cpu().numpy(), mu2.cpu().numpy()) < 1e-12
+
+
+def test_short_paths_one_cta_per_path_kernel(monkeypatch):
+    """N <= 112 (the reference resamples trajectories to 33 points, GPmap.py:189): the whole fit runs in one CTA per
+    path.  Against the oracle, against the tiled pipeline (GPM_NO_SMALL_FUSED), with per-path hyper-parameters, and
+    the LAPACK-style info of a path that is not positive definite."""
+    for (B, N, D, R) in ((7, 33, 2, 2), (3, 1, 2, 1), (4, 2, 3, 2), (5, 64, 3, 3), (3, 100, 2, 8), (6, 112, 3, 2)):
+        Xb, Yb, th = wl.batched_paths(B, max(N, 4), seed=11, D=D, R=2)
+        Xb, Yb = np.ascontiguousarray(Xb[:, :N]), Yb[:, :N]
+        rng = np.random.default_rng(N)
+        Yb = np.ascontiguousarray(np.concatenate([Yb, rng.standard_normal((B, N, 6))], axis=2)[:, :, :R])
+        monkeypatch.delenv("GPM_NO_SMALL_FUSED", raising=False)
+        a1, l1 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+        monkeypatch.setenv("GPM_NO_SMALL_FUSED", "1")
+        a0, l0 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+        monkeypatch.delenv("GPM_NO_SMALL_FUSED", raising=False)
+        a_o, l_o = gp_ref.fit_batched(Xb, Yb, th)
+        assert nrm(a1.cpu().numpy(), a_o) < MEAN_TOL
+        assert np.abs(l1.cpu().numpy() - l_o).max() < LML_TOL * max(np.abs(l_o).max(), 1.0)
+        assert nrm(a1.cpu().numpy(), a0.cpu().numpy()) < 1e-10
+        assert np.abs((l1 - l0).cpu().numpy()).max() < 1e-11 * max(np.abs(l_o).max(), 1.0)
+    # per-path hyper-parameters
+    Xb, Yb, th = wl.batched_paths(5, 33, seed=12, D=2, R=2)
+    ths = np.stack([th * np.array([1.0 + 0.1 * b, 1.0 + 0.1 * b, 1.0 + 0.05 * b, 1.0 + b]) for b in range(5)])
+    a1, l1 = GPmap.fit_gp_batched(Xb, Yb, theta=ths)
+    a_o, l_o = gp_ref.fit_batched(Xb, Yb, ths)
+    assert nrm(a1.cpu().numpy(), a_o) < MEAN_TOL
+    assert np.abs(l1.cpu().numpy() - l_o).max() < LML_TOL * np.abs(l_o).max()
+    # a duplicated sample with zero noise makes K singular: the path is reported, the others are unaffected
+    Xs = Xb.copy(); Xs[2, 20] = Xs[2, 5]
+    th0 = th.copy(); th0[-1] = 0.0
+    with pytest.raises(np.linalg.LinAlgError, match="path 2"):
+        GPmap.fit_gp_batched(Xs, Yb, theta=th0)
+    # many more paths than gridDim.y allows for the tiled pipeline
+    Xm, Ym, thm = wl.batched_paths(70000, 8, seed=13, D=2, R=1)
+    am, lm = GPmap.fit_gp_batched(Xm, Ym, theta=thm)
+    a_o, l_o = gp_ref.fit_batched(Xm[-3:], Ym[-3:], thm)
+    assert nrm(am[-3:].cpu().numpy(), a_o) < MEAN_TOL and bool(torch.isfinite(lm).all())
