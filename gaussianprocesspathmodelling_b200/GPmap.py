@@ -244,7 +244,10 @@ def fit_gp(X, Y, lengthscale=None, signal_var=1.0, noise_var=1e-2, theta=None, c
 
 
 def fit_gp_batched(Xb, Yb, lengthscale=None, signal_var=1.0, noise_var=1e-2, theta=None, check=True):
-    """B independent equal-length paths: Xb (B, N, D), Yb (B, N, R) -> alpha (B, N, R), lml (B, R) (CUDA)."""
+    """B independent equal-length paths: Xb (B, N, D), Yb (B, N, R) -> alpha (B, N, R), lml (B, R) (CUDA).
+
+    Paths of up to 112 samples (the reference resamples to 33, GPmap.py:189) are fitted one CTA per path entirely in
+    shared memory; longer ones go through the tiled tensor-core pipeline (B <= 65535 there)."""
     torch = _torch()
     lib = _native.load()
     Xb = _dev(Xb)

@@ -1,6 +1,7 @@
-// Batched per-path fits: B independent paths of equal length N.  All paths advance together
-// through batched launches (grid.y = path) of the same kernels the single-matrix path uses:
-// covariance (lower tiles) -> blocked Cholesky with look-ahead -> blocked solves -> LML.
+// Batched per-path fits: B independent paths of equal length N.
+//   N <= 112 (the reference's 33-point trajectories): one CTA per path, the whole fit in shared memory (small.cu).
+//   longer paths: all paths advance together through batched launches (grid.y = path) of the same kernels the
+//   single-matrix path uses: covariance (lower tiles) -> blocked Cholesky -> blocked solves -> LML.
 #include <stdlib.h>
 
 #include "gemm.cuh"
