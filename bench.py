@@ -151,6 +151,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is the CPU path on ALL the host cores
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:                                        # noqa: BLE001
+        pass
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_sample(2048)
     vals, det = [], None
