@@ -52,12 +52,12 @@ def load_peaks():
 
 def ncu_traffic():
     """DRAM bytes (read + write) of the dominant launch -- the fused variance sweep of gemm_nt_kernel -- from the
-    committed `ncu --set full` capture of the same workload (profiles/r01_final_ncu_gemm_summary.json)."""
+    committed `ncu --set full` capture of the same workload (profiles/r01_final2_ncu_gemm_summary.json)."""
     try:
-        s = json.load(open(os.path.join(ROOT, "profiles", "r01_final_ncu_gemm_summary.json")))
+        s = json.load(open(os.path.join(ROOT, "profiles", "r01_final2_ncu_gemm_summary.json")))
         return {"bytes_per_launch": s["dram_read_bytes"] + s["dram_write_bytes"],
                 "algorithmic_operand_bytes": s["algorithmic_operand_bytes"], "duration_ms_under_ncu": s["duration_ms"],
-                "dmma_pipe_active_pct": s["dmma_pipe_active_pct"], "source": "profiles/r01_final_ncu_gemm_summary.json"}
+                "dmma_pipe_active_pct": s["dmma_pipe_active_pct"], "source": "profiles/r01_final2_ncu_gemm_summary.json"}
     except Exception:
         return None
 
