@@ -53,15 +53,18 @@ fit_small_kernel(const double* __restrict__ Xb, const double* __restrict__ Yb, i
   for (int r = 0; r < RR; r++) y0[r] = y[r] = (i < N && r < R) ? Y[i * R + r] : 0.0;
   __syncthreads();
 
-  // ---- covariance: rows dealt to warps, columns to lanes (same arithmetic as cov_kernel) ----
-  for (int r = warp; r < N; r += nwarp) {
+  // ---- covariance: the N(N+1)/2 entries of the lower triangle dealt evenly to the threads (same arithmetic as
+  //      cov_kernel) ----
+  for (int e = tid; e < tri(N); e += nthr) {
+    int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+    while (tri(r + 1) <= e) r++;
+    while (tri(r) > e) r--;
+    const int c = e - tri(r);
     const double a[3] = {xs[r * 3], xs[r * 3 + 1], D == 3 ? xs[r * 3 + 2] : 0.0};
-    for (int c = lane; c <= r; c += 32) {
-      const double bq[3] = {xs[c * 3], xs[c * 3 + 1], D == 3 ? xs[c * 3 + 2] : 0.0};
-      double v = rbf<D>(a, bq, th.sf2);
-      if (c == r) v += th.sn2;
-      Kp[tri(r) + c] = v;
-    }
+    const double bq[3] = {xs[c * 3], xs[c * 3 + 1], D == 3 ? xs[c * 3 + 2] : 0.0};
+    double v = rbf<D>(a, bq, th.sf2);
+    if (c == r) v += th.sn2;
+    Kp[e] = v;
   }
   __syncthreads();
 
