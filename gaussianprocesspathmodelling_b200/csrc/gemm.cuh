@@ -51,6 +51,12 @@ struct GemmArgs {
   long long rhs_r_row0;   // first row of the residual block of tile ti = 0
   long long rhs_rows_end; // rows per matrix (exclusive bound for the residual rows)
   long long batch_rhs_rows;
+  // raw operand pointers (optional): with them a launch of at most 37 tiles on one matrix takes the latency
+  // kernel of gemm_small.cu (four 64 x 64 quarters per tile, bitwise the same arithmetic)
+  const double* small_A;
+  const double* small_B;
+  long long small_lda, small_ldb;
+  long long small_a_rows_end, small_b_rows_end;   // rows of the matrices behind A and B (reads are clamped to them)
 #ifdef GPM_GEMM_TIMING
   int dbg_launch;         // instrumentation builds: slot of this launch in the phase-stamp table
 #endif
@@ -64,6 +70,9 @@ inline int gemm_grid_x(const GemmArgs& a) {
 }
 
 // mapC describes the matrix args.C points into (used to prefetch C tiles by TMA when epi == EPI_SUB)
+bool gemm_small_eligible(const GemmArgs& a, int batch);
+int launch_gemm_small(gpm_handle_impl* h, const GemmArgs& a, cudaStream_t stream);
+
 int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& mapB,
                 const CUtensorMap& mapC, const GemmArgs& args, int batch, cudaStream_t stream,
                 const CUtensorMap* mapB2 = nullptr);

@@ -543,6 +543,8 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
     a.c_rows_end = N; a.c_cols_end = (long long)(k + 1) * NB;
     a.epi = EPI_STORE;
     a.tri_b = 1;                                   // inv(L_kk) is lower triangular
+    a.small_A = K; a.small_lda = ldk; a.small_a_rows_end = total_rows;
+    a.small_B = invD; a.small_ldb = NB; a.small_b_rows_end = (long long)batch * nblk * NB;
     if (rhs_r) {
       a.rhs_r = rhs_r; a.rhs_z = rhs_z; a.rhs_R = R;
       a.rhs_z_row0 = (long long)k * NB; a.rhs_r_row0 = (long long)(k + 1) * NB;
@@ -561,6 +563,7 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
     a.c_rows_end = N; a.c_cols_end = N;
     a.epi = EPI_SUB;
     a.diag_lower = 1;                           // tile (0,0) / tiles ti == tj are L L^T: lower triangle only
+    a.small_A = K; a.small_B = K; a.small_lda = a.small_ldb = ldk; a.small_a_rows_end = a.small_b_rows_end = total_rows;
     a.batch_a_rows = batch_rows; a.batch_b_rows = batch_rows; a.batch_c_rows = batch_rows;
     if (jhi - jlo == 1) {                       // a single tile column: rows jlo .. nblk-1
       a.tri = 0; a.tiles_m = nblk - jlo; a.tiles_n = 1;

@@ -608,3 +608,23 @@ def test_short_paths_one_cta_per_path_kernel(monkeypatch):
     am, lm = GPmap.fit_gp_batched(Xm, Ym, theta=thm)
     a_o, l_o = gp_ref.fit_batched(Xm[-3:], Ym[-3:], thm)
     assert nrm(am[-3:].cpu().numpy(), a_o) < MEAN_TOL and bool(torch.isfinite(lm).all())
+
+
+def test_latency_tile_kernel_is_bitwise_the_tile_kernel(monkeypatch):
+    """Launches of at most 37 tiles (every tile launch of a fit with N <= 4096, the tail of a large one) split each
+    128x128 tile into four 64x64 quarters on four SMs (gemm_small.cu).  Same DMMA sequence per element: the factor must
+    not change by a single bit, for full and ragged last blocks."""
+    for N in (129, 900, 2048, 4096 + 77):
+        X, _, th = wl.single_path(N, seed=7, D=2)
+        Ko = gp_ref.cov(X, th)
+        monkeypatch.delenv("GPM_NO_SMALL_TILES", raising=False)
+        L1, ws1, info1 = gpu_potrf(Ko)
+        monkeypatch.setenv("GPM_NO_SMALL_TILES", "1")
+        L0, ws0, info0 = gpu_potrf(Ko)
+        monkeypatch.delenv("GPM_NO_SMALL_TILES", raising=False)
+        assert info1 == 0 and info0 == 0
+        assert np.array_equal(L1, L0)
+        assert torch.equal(ws1, ws0)
+        if N <= 2048:
+            Lo = scipy.linalg.cholesky(Ko, lower=True)
+            assert nrm(L1, Lo) < 1e-9
