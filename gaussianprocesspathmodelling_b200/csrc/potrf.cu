@@ -127,43 +127,6 @@ __device__ __forceinline__ int chol8_tile(double* sm, int tb0, double* l8, doubl
   return bad;
 }
 
-// The same 8x8 factorisation by the first eight lanes of ONE WARP, lane i owning row i (all 32 lanes must call;
-// lanes 8..31 shadow lanes 0..7 and write nothing).  Right-looking: per pivot one shuffle for the pivot, one rsqrt,
-// one multiply, seven (independent) shuffles for the scaled column and one FMA per trailing entry -- a dependent chain
-// of ~130 cycles per pivot instead of the ~220 the single thread needs to issue its ~50 instructions per pivot.
-// Every element sees exactly the operations of chol8_tile (products -l_ij * l_cj accumulated for increasing j, then
-// one scaling by 1/L_jj), so the factor is bitwise the same.
-__device__ __forceinline__ int chol8_tile_warp(double* sm, int tb0, double* l8, double* rd8, int lane) {
-  const int i = lane & 7;
-  double a[8];
-#pragma unroll
-  for (int c = 0; c < 8; c++) a[c] = (c <= i) ? sm[tb0 + in_tile(i, c)] : 0.0;
-  int bad = 0;
-  double myr = 0.0;
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    double d = __shfl_sync(0xffffffffu, a[j], j);          // pivot: entry (j, j) after the updates so far
-    if (!(d > 0.0) || !(d < 1.0e300)) { if (!bad) bad = j + 1; d = 1.0; }
-    const double r = rsqrt(d);
-    const double lij = (i == j) ? d * r : a[j] * r;          // column j of L (zero above the diagonal)
-    a[j] = lij;
-    if (i == j) myr = r;
-#pragma unroll
-    for (int c = 0; c < 8; c++)
-      if (c > j) {
-        const double lcj = __shfl_sync(0xffffffffu, lij, c);
-        if (c <= i) a[c] = fma(-lij, lcj, a[c]);
-      }
-  }
-  if (lane < 8) {
-    rd8[i] = myr;
-#pragma unroll
-    for (int c = 0; c < 8; c++)
-      if (c <= i) { sm[tb0 + in_tile(i, c)] = a[c]; l8[i * (i + 1) / 2 + c] = a[c]; }
-  }
-  return bad;
-}
-
 // One level of the recursive-doubling inverse on DMMA tiles:  X21 = -X22 * (L21 * X11)  for all
 // 64/S pairs of SxS diagonal blocks (X11, X22 already inverted in place, upper parts zero).
 // Only tiles on or below the diagonal are touched (they are the only ones stored).  Each 8x8 result tile
@@ -315,9 +278,9 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
   const int x_in = g * 8 + (q ^ (((g >> 1) & 1) << 2));          // panel fragment: row g, column q
   const int x4 = (x_in ^ 4) - x_in;                               // ... and column q + 4
   constexpr int UW = P2_WARPS - 1;                                // update warps; warp UW looks ahead
-  if (warp == 0) {
-    const int bad = chol8_tile_warp(sm, tile_base(0, 0), l8, rd, lane);
-    if (lane == 0 && bad && bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + bad));
+  if (tid == 0) {
+    const int bad = chol8_tile(sm, tile_base(0, 0), l8, rd);
+    if (bad && bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + bad));
   }
   __syncthreads();
   for (int p = 0; p < 16; p++) {
@@ -357,9 +320,9 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
       dmma(c.x, c.y, -b1, b1);
       *cp = c;
       __syncwarp();
-      {
-        const int bad = chol8_tile_warp(sm, tile_base(rbt, rbt), l8, rd + c0 + 8, lane);
-        if (lane == 0 && bad && c0 + 8 + bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + c0 + 8 + bad));
+      if (lane == 0) {
+        const int bad = chol8_tile(sm, tile_base(rbt, rbt), l8, rd + c0 + 8);
+        if (bad && c0 + 8 + bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + c0 + 8 + bad));
       }
     } else {
       // contiguous chunk of tiles per warp: consecutive tiles share their row, so the A fragments are
