@@ -590,10 +590,11 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
 
   // Outer panels: wide panels make the trailing updates deep (K = 256 or 512: less C traffic and the tile
   // prologue/epilogue amortised over more slabs) but lengthen the serial panel chain, which must stay
-  // hidden behind the rest-update: width 8 while >= 96 block columns remain, 4 while >= 64, 2 while >= 48,
-  // then 1 (thresholds swept on B200 at N = 8192 and 16384, tools/potrf_sweep.sh).
+  // hidden behind the rest-update: width 8 while >= 96 block columns remain, 4 while >= 64, 2 while >= 32,
+  // then 1 (thresholds swept on B200 at N = 8192 and 16384, tools/potrf_sweep.sh and potrf_sweep2.sh; the response
+  // is flat within 1 % around these values).
   // Large batches are throughput-bound in every launch, so they use width 2 and no look-ahead.
-  static const int wide_env = getenv("GPM_WIDE_MIN") ? atoi(getenv("GPM_WIDE_MIN")) : 48;
+  static const int wide_env = getenv("GPM_WIDE_MIN") ? atoi(getenv("GPM_WIDE_MIN")) : 32;
   static const int wide4_env = getenv("GPM_WIDE4_MIN") ? atoi(getenv("GPM_WIDE4_MIN")) : 64;
   static const int wide8_env = getenv("GPM_WIDE8_MIN") ? atoi(getenv("GPM_WIDE8_MIN")) : 96;
   std::vector<int> pb(nblk + 1), pw(nblk + 1);
