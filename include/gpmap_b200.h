@@ -111,7 +111,9 @@ int gpm_predict(gpm_handle_t h, const double* X, int64_t N, int32_t D, const dou
  * length).  Xb: B x N x D, Yb: B x N x R, theta: HOST pointer to (D+2) doubles shared by all
  * paths (theta_stride = 0) or to B x (D+2) per-path values (theta_stride = D+2; the host array must stay
  * valid until the copy enqueued on `stream` has run).  alpha: B x N x R (must not alias Yb), lml: B x R,
- * info: B device int32.  ws: gpm_fit_batched_workspace_bytes(B, N) bytes. */
+ * info: B device int32.  ws: gpm_fit_batched_workspace_bytes(B, N) bytes.
+ * Paths of N <= 112 samples (GPmap.py:189 resamples every trajectory to 33) are fitted one CTA per path entirely in
+ * shared memory and B is limited only by 2^31; longer paths go through batched tile launches with B <= 65535. */
 size_t gpm_fit_batched_workspace_bytes(int64_t B, int64_t N);
 int gpm_fit_batched(gpm_handle_t h, const double* Xb, const double* Yb, int64_t B, int64_t N,
                     int32_t D, int32_t R, const double* theta, int64_t theta_stride,
