@@ -395,6 +395,11 @@ def run_b200(args):
     }
     for k in kernels.values():
         k["frac"] = (k["achieved"] / k["peak"]) if k["peak"] else None
+    # at N=4096 these three are latency chains, not throughput kernels: say so next to the fractions
+    kernels["cov_full"]["note"] = "134 MB in ~35 us: launch ramp dominates; the N=16384 figure is extra.cfg4_N16384.cov_frac_hbm"
+    kernels["potrf"]["note"] = ("32 block columns x (potf2 ~35 us + two latency-kernel launches ~10 us each): chain-bound; "
+                                "the N=16384 figure is extra.cfg4_N16384.potrf_frac_dgemm")
+    kernels["solve_lml"]["note"] = "2 x 32 flag-chained hand-offs of ~5 us: chain-bound; N=16384: extra.cfg4_N16384.solve_gbs"
 
     extra = {"phases_ms": phases, "kernels": kernels, "potrf_info": info}
 
