@@ -160,3 +160,18 @@ def test_lml_grad_matches_finite_differences():
         tp[j] *= np.exp(h); tm[j] *= np.exp(-h)
         fd = (gp_ref.fit(X, Y, tp)["lml"] - gp_ref.fit(X, Y, tm)["lml"]) / (2 * h)
         assert np.allclose(g[:, j], fd, rtol=2e-6, atol=1e-6 * np.abs(g).max())
+
+
+def test_separable_form_of_the_rbf_kernel_stays_within_a_few_ulp():
+    """The grid kernels evaluate k = exp(-dx^2/2) * (sf2 exp(-dy^2/2)) instead of sf2 exp(-(dx^2+dy^2)/2)
+    (csrc/cov.cu: cross_cov_grid_kernel, predict_mean_grid_kernel).  In exact arithmetic they are equal; in float64
+    the two differ by a few ulp over the whole range of scaled distances of the workloads (|d| <= 100/8 * sqrt 2)."""
+    rng = np.random.default_rng(0)
+    dx = rng.uniform(-12.5, 12.5, 200000)
+    dy = rng.uniform(-12.5, 12.5, 200000)
+    sf2 = 1.7
+    joint = sf2 * np.exp(-0.5 * (dx * dx + dy * dy))
+    sep = np.exp(-0.5 * (dx * dx)) * (sf2 * np.exp(-0.5 * (dy * dy)))
+    ok = joint > 1e-300
+    rel = np.abs(sep[ok] - joint[ok]) / joint[ok]
+    assert rel.max() < 8 * np.finfo(np.float64).eps
