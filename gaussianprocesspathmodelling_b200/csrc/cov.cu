@@ -237,8 +237,9 @@ predict_mean_kernel(const double* __restrict__ X, long long N, Theta th, const d
 // per training point instead of PA * PB.  The two kernels below evaluate the factors on the fly per patch (no
 // tables in HBM): the materialised cross-covariance becomes a pure HBM-write stream and the mean an FMA loop.
 // A query's value does not depend on which patch or launch it falls into (bitwise), so sharded ranges
-// concatenate exactly.  The product of two correctly rounded factors differs from the single exponential of
-// the oracle by at most ~2 ulp.
+// concatenate exactly.  Both forms carry the rounding of their exponents (|arg| eps relative), so the product agrees
+// with the single exponential of the oracle to (|arg| + 4) eps relative and a few eps * sf2 absolute
+// (tests/test_oracle.py).
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ double grid_x(const gpm_grid_t& g, long long ix) {
   const double sx = g.gx > 1 ? (g.x1 - g.x0) / (double)(g.gx - 1) : 0.0;

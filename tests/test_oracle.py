@@ -162,16 +162,19 @@ def test_lml_grad_matches_finite_differences():
         assert np.allclose(g[:, j], fd, rtol=2e-6, atol=1e-6 * np.abs(g).max())
 
 
-def test_separable_form_of_the_rbf_kernel_stays_within_a_few_ulp():
+def test_separable_form_of_the_rbf_kernel_agrees_to_argument_rounding():
     """The grid kernels evaluate k = exp(-dx^2/2) * (sf2 exp(-dy^2/2)) instead of sf2 exp(-(dx^2+dy^2)/2)
     (csrc/cov.cu: cross_cov_grid_kernel, predict_mean_grid_kernel).  In exact arithmetic they are equal; in float64
-    the two differ by a few ulp over the whole range of scaled distances of the workloads (|d| <= 100/8 * sqrt 2)."""
+    each form carries the rounding of its exponent(s), |arg| * eps relative, so the two agree to (|arg| + 4) eps
+    relative (1.5e-14 at |arg| = 150, where k ~ 1e-65) and to a few eps * sf2 in absolute terms -- against tolerances of
+    1e-8 (mean) and 1e-6 (variance)."""
     rng = np.random.default_rng(0)
-    dx = rng.uniform(-12.5, 12.5, 200000)
+    dx = rng.uniform(-12.5, 12.5, 200000)          # scaled distances of the workloads: |d| <= 100/8 per axis
     dy = rng.uniform(-12.5, 12.5, 200000)
     sf2 = 1.7
-    joint = sf2 * np.exp(-0.5 * (dx * dx + dy * dy))
+    arg = 0.5 * (dx * dx + dy * dy)
+    joint = sf2 * np.exp(-arg)
     sep = np.exp(-0.5 * (dx * dx)) * (sf2 * np.exp(-0.5 * (dy * dy)))
-    ok = joint > 1e-300
-    rel = np.abs(sep[ok] - joint[ok]) / joint[ok]
-    assert rel.max() < 8 * np.finfo(np.float64).eps
+    eps = np.finfo(np.float64).eps
+    assert np.all(np.abs(sep - joint) <= (arg + 4.0) * eps * joint)
+    assert np.abs(sep - joint).max() <= 4 * eps * sf2
