@@ -238,8 +238,8 @@ predict_mean_kernel(const double* __restrict__ X, long long N, Theta th, const d
 // tables in HBM): the materialised cross-covariance becomes a pure HBM-write stream and the mean an FMA loop.
 // A query's value does not depend on which patch or launch it falls into (bitwise), so sharded ranges
 // concatenate exactly.  Both forms carry the rounding of their exponents (|arg| eps relative), so the product agrees
-// with the single exponential of the oracle to (|arg| + 4) eps relative and a few eps * sf2 absolute
-// (tests/test_oracle.py).
+// with the single exponential of the oracle to (|arg| + 4) eps relative and a few eps * sf2 absolute (a CPU test
+// pins that bound).
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ double grid_x(const gpm_grid_t& g, long long ix) {
   const double sx = g.gx > 1 ? (g.x1 - g.x0) / (double)(g.gx - 1) : 0.0;
