@@ -26,7 +26,8 @@ import numpy as np
 from . import _native
 
 __all__ = ["trajectory", "trajectories", "trajs", "check_if_valid_trajectory", "readcsvfile",
-           "fit_gp", "GPModel", "fit_gp_batched", "lml_sweep", "make_theta", "export_raster", "optimize_gp"]
+           "fit_gp", "GPModel", "fit_gp_batched", "lml_sweep", "make_theta", "export_raster", "optimize_gp",
+           "clear_workspaces"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -40,18 +41,89 @@ def _torch():
     return torch
 
 
+class _Stager:
+    """Cached pinned staging buffers for host -> device copies (a fresh ``pin_memory()`` per call costs a
+    ``cudaHostAlloc``).  A small ring of grow-only pinned buffers per device; a slot is reused only after the
+    copy that last read it has completed (one event per slot)."""
+    SLOTS = 4
+
+    def __init__(self):
+        self.slots = {}          # device index -> list of [pinned uint8 tensor | None, event | None]
+        self.next = {}
+
+    def to_device(self, arr, device):
+        torch = _torch()
+        dev = torch.device(device if device is not None else "cuda")
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        ring = self.slots.setdefault(idx, [[None, None] for _ in range(self.SLOTS)])
+        k = self.next.get(idx, 0)
+        self.next[idx] = (k + 1) % self.SLOTS
+        slot = ring[k]
+        nbytes = arr.nbytes
+        if slot[1] is not None:
+            slot[1].synchronize()                      # the previous copy out of this slot has finished
+        if slot[0] is None or slot[0].numel() < nbytes:
+            slot[0] = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+        host = slot[0][:nbytes].view(torch.float64).view(arr.shape)
+        host.numpy()[...] = arr                        # one host memcpy into pinned memory
+        out = host.to(torch.device("cuda", idx), non_blocking=True)
+        if slot[1] is None:
+            slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream(idx))
+        return out
+
+
+_stager = _Stager()
+
+
 def _dev(a, device=None):
-    """float64 contiguous CUDA tensor from a numpy array / sequence / tensor (zero-copy when already so)."""
+    """float64 contiguous CUDA tensor from a numpy array / sequence / tensor (zero-copy when already so).
+    Host data goes through cached pinned staging buffers (one host memcpy + one asynchronous H2D copy)."""
     torch = _torch()
     if isinstance(a, torch.Tensor):
         t = a
         if t.dtype != torch.float64:
             t = t.double()
-        if not t.is_cuda:
-            t = t.pin_memory().to(device or "cuda", non_blocking=True)
-        return t.contiguous()
+        if t.is_cuda:
+            return t.contiguous()
+        if t.is_pinned():
+            return t.contiguous().to(device or "cuda", non_blocking=True)
+        a = t.contiguous().numpy()
     arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
-    return torch.from_numpy(arr).pin_memory().to(device or "cuda", non_blocking=True)
+    if arr.size == 0:
+        return torch.empty(arr.shape, dtype=torch.float64, device=device or "cuda")
+    return _stager.to_device(arr, device)
+
+
+# Scratch workspaces (the variance sweep's K*^T / W buffer, the batched fits' scratch) are cached per
+# (device, stream, tag) and grow on demand, so repeated calls -- a sweep, a serving loop, a benchmark -- do not
+# re-allocate gigabytes per call.  Work on different streams never shares a buffer.  ``workspace=`` arguments of
+# the public functions override the cache with a caller-owned float64 CUDA tensor.
+_workspaces = {}
+PREDICT_WORKSPACE_BYTES = 4 << 30       # default cap of the variance workspace (queries are processed in chunks)
+
+
+def _workspace(nbytes, device, tag, given=None):
+    torch = _torch()
+    if given is not None:
+        if not (isinstance(given, torch.Tensor) and given.is_cuda and given.dtype == torch.float64 and
+                given.is_contiguous()):
+            raise ValueError("workspace must be a contiguous float64 CUDA tensor")
+        return given
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream, tag)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() * 8 < nbytes:
+        _workspaces.pop(key, None)
+        ws = None
+        ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def clear_workspaces():
+    """Release every cached scratch workspace (device memory goes back to PyTorch's allocator)."""
+    _workspaces.clear()
 
 
 def _stream(t):
@@ -79,7 +151,6 @@ class GPModel:
 
     def __init__(self, X, theta, K, ws, alpha, lml, info):
         self.X, self.theta, self.K, self.ws, self.alpha, self.lml_dev, self.info = X, theta, K, ws, alpha, lml, info
-        self._pws = None
 
     @property
     def N(self):
@@ -136,23 +207,27 @@ class GPModel:
         return grad.cpu().numpy()
 
     # -- prediction ---------------------------------------------------------------------------
-    def _predict(self, Xs, grid, m0, m1, return_var, include_noise):
+    def _predict(self, Xs, grid, m0, m1, return_var, include_noise, workspace=None, out=None):
         torch = _torch()
         lib = _native.load()
         h = _native.handle(self.X.device.index or 0)
         M = m1 - m0
         R = self.alpha.shape[1]
-        mu = torch.empty((M, R), dtype=torch.float64, device=self.X.device)
-        var = torch.empty((M,), dtype=torch.float64, device=self.X.device) if return_var else None
+        if out is not None:                  # caller-owned result buffers (e.g. slices of an all-gather buffer)
+            mu, var = (out if return_var else (out, None))
+            if mu.shape != (M, R) or not mu.is_contiguous() or (return_var and (var.shape != (M,) or not var.is_contiguous())):
+                raise ValueError("out= buffers must be contiguous with shapes (M, R) and (M,)")
+        else:
+            mu = torch.empty((M, R), dtype=torch.float64, device=self.X.device)
+            var = torch.empty((M,), dtype=torch.float64, device=self.X.device) if return_var else None
         flags = _native.PREDICT_MEAN | (_native.PREDICT_VAR if return_var else 0) | \
             (_native.PREDICT_ADD_NOISE if include_noise else 0)
         ws, nbytes = None, 0
         if return_var and M > 0:
-            nbytes = int(lib.gpm_predict_workspace_bytes(h, self.N, M))
-            if self._pws is None or self._pws.numel() * 8 < nbytes:
-                self._pws = None
-                self._pws = torch.empty(nbytes // 8, dtype=torch.float64, device=self.X.device)
-            ws = self._pws
+            # the library sizes W for all M queries; cap it (queries are then processed in chunks of whole waves)
+            nbytes = min(int(lib.gpm_predict_workspace_bytes(h, self.N, M)),
+                         max(PREDICT_WORKSPACE_BYTES, int(lib.gpm_predict_workspace_bytes(h, self.N, 128 * 148))))
+            ws = _workspace(nbytes, self.X.device, "predict", workspace)
             nbytes = ws.numel() * 8
         g = C.byref(grid) if grid is not None else None
         rc = lib.gpm_predict(h, _ptr(self.X), self.N, self.D, _native.theta_array(self.theta), _ptr(self.K),
@@ -161,25 +236,30 @@ class GPModel:
         _native.check(rc, "gpm_predict")
         return (mu, var) if return_var else mu
 
-    def predict(self, Xs, return_var=True, include_noise=False):
-        """Posterior at arbitrary query points Xs (M, D): mu (M, R)[, var (M,)] as CUDA tensors."""
+    def predict(self, Xs, return_var=True, include_noise=False, workspace=None):
+        """Posterior at arbitrary query points Xs (M, D): mu (M, R)[, var (M,)] as CUDA tensors.
+        The variance (signal_var - ||L^-1 k*||^2) is clamped at 0: cancellation next to training points could
+        otherwise return values of order -1e-16 signal_var."""
         Xs = _dev(Xs, self.X.device)
         if Xs.ndim != 2 or Xs.shape[1] != self.D:
             raise ValueError(f"Xs must be (M, {self.D})")
-        return self._predict(Xs, None, 0, Xs.shape[0], return_var, include_noise)
+        return self._predict(Xs, None, 0, Xs.shape[0], return_var, include_noise, workspace)
 
-    def predict_grid(self, bounds, shape, t=None, return_var=True, include_noise=False, points=None):
+    def predict_grid(self, bounds, shape, t=None, return_var=True, include_noise=False, points=None,
+                     workspace=None, out=None):
         """Posterior on a regular grid (``indexing='xy'``, y outer).  bounds = (x0, x1, y0, y1),
         shape = (Gx, Gy).  Returns mu (Gy, Gx, R)[, var (Gy, Gx)]; with ``points=(m0, m1)`` only that
         flat range of grid points is evaluated and flat (m1-m0, R) / (m1-m0,) tensors are returned
-        (this is how the grid is sharded across GPUs)."""
+        (this is how the grid is sharded across GPUs).  ``workspace``: caller-owned scratch (float64 CUDA tensor;
+        default: a cached per-stream buffer of at most PREDICT_WORKSPACE_BYTES).  ``out=(mu, var)``: write the
+        results of a ``points`` range into caller-owned flat buffers."""
         x0, x1, y0, y1 = [float(v) for v in bounds]
         Gx, Gy = int(shape[0]), int(shape[1])
         if self.D == 3 and t is None:
             raise ValueError("a D=3 model needs the query time t")
         grid = _native.GpmGrid(x0, x1, y0, y1, float(t) if t is not None else 0.0, Gx, Gy)
         m0, m1 = (0, Gx * Gy) if points is None else (int(points[0]), int(points[1]))
-        out = self._predict(None, grid, m0, m1, return_var, include_noise)
+        out = self._predict(None, grid, m0, m1, return_var, include_noise, workspace, out)
         if points is not None:
             return out
         if return_var:
@@ -231,7 +311,7 @@ def fit_gp(X, Y, lengthscale=None, signal_var=1.0, noise_var=1e-2, theta=None, c
     ws = torch.empty(int(lib.gpm_potrf_workspace_bytes(N)) // 8, dtype=torch.float64, device=X.device)
     info = torch.zeros(1, dtype=torch.int32, device=X.device)
     alpha = torch.empty((N, R), dtype=torch.float64, device=X.device)
-    lml_dev = torch.empty((R,), dtype=torch.float64, device=X.device)
+    lml_dev = torch.full((R,), float("nan"), dtype=torch.float64, device=X.device)    # stays NaN with lml=False
     th = _native.theta_array(theta)
     _native.check(lib.gpm_cov(h, _ptr(X), N, D, th, _ptr(K), ld, _native.COV_LOWER, st), "gpm_cov")
     _native.check(lib.gpm_potrf(h, _ptr(K), N, ld, _ptr(ws), _ptr(info), st), "gpm_potrf")
@@ -243,7 +323,7 @@ def fit_gp(X, Y, lengthscale=None, signal_var=1.0, noise_var=1e-2, theta=None, c
     return model
 
 
-def fit_gp_batched(Xb, Yb, lengthscale=None, signal_var=1.0, noise_var=1e-2, theta=None, check=True):
+def fit_gp_batched(Xb, Yb, lengthscale=None, signal_var=1.0, noise_var=1e-2, theta=None, check=True, workspace=None):
     """B independent equal-length paths: Xb (B, N, D), Yb (B, N, R) -> alpha (B, N, R), lml (B, R) (CUDA).
 
     Paths of up to 112 samples (the reference resamples to 33, GPmap.py:189) are fitted one CTA per path entirely in
@@ -266,7 +346,7 @@ def fit_gp_batched(Xb, Yb, lengthscale=None, signal_var=1.0, noise_var=1e-2, the
     alpha = torch.empty((B, N, R), dtype=torch.float64, device=Xb.device)
     lml = torch.empty((B, R), dtype=torch.float64, device=Xb.device)
     info = torch.zeros(B, dtype=torch.int32, device=Xb.device)
-    ws = torch.empty(int(lib.gpm_fit_batched_workspace_bytes(B, N)) // 8, dtype=torch.float64, device=Xb.device)
+    ws = _workspace(int(lib.gpm_fit_batched_workspace_bytes(h, B, N)), Xb.device, "fit_batched", workspace)
     th_arr = _native.theta_array(theta.ravel())
     rc = lib.gpm_fit_batched(h, _ptr(Xb), _ptr(Yb), B, N, D, R, th_arr, stride,
                              _ptr(alpha), _ptr(lml), _ptr(info), _ptr(ws), _stream(Xb))
@@ -401,38 +481,56 @@ class trajectories:
         keys = list(self.pathdict.keys()) if keys is None else list(keys)
         return np.stack([self.pathdict[k].gp_inputs(use_time) for k in keys]), keys
 
-    # -- k-means (GPmap.py:36-93); the assignment step runs on the GPU ---------------------------
+    # -- k-means (GPmap.py:36-93): assignment + centroid update + convergence test run on the GPU ----------
+    def _upload_paths(self, keys):
+        """One host -> device copy of all paths: (3, P, n) = xs, ys, timestamp planes, path-major; the
+        sample-major (n, P) copies the assignment kernel reads are made on the device."""
+        host = np.stack([np.stack([self.pathdict[k].xs for k in keys]),
+                         np.stack([self.pathdict[k].ys for k in keys]),
+                         np.stack([self.pathdict[k].timestamp for k in keys])])
+        dev = _dev(host)
+        pxT, pyT = dev[0].t().contiguous(), dev[1].t().contiguous()
+        return dev, pxT, pyT
+
     def _assign(self, keys, centroids):
+        """One assignment step (GPmap.py:72-80): returns (assign (P,), dist (P, k)) as numpy arrays."""
         torch = _torch()
         lib = _native.load()
-        px = _dev(np.stack([self.pathdict[k].xs for k in keys]))
-        py = _dev(np.stack([self.pathdict[k].ys for k in keys]), px.device)
-        cx = _dev(np.stack([c.xs for c in centroids]), px.device)
-        cy = _dev(np.stack([c.ys for c in centroids]), px.device)
-        P, n = px.shape
+        dev, pxT, pyT = self._upload_paths(keys)
+        cx = _dev(np.stack([c.xs for c in centroids]), dev.device)
+        cy = _dev(np.stack([c.ys for c in centroids]), dev.device)
+        _, P, n = dev.shape
         k = cx.shape[0]
-        dist = torch.empty((P, k), dtype=torch.float64, device=px.device)
-        assign = torch.empty((P,), dtype=torch.int32, device=px.device)
-        h = _native.handle(px.device.index or 0)
-        rc = lib.gpm_kmeans_assign(h, _ptr(px), _ptr(py), P, n, _ptr(cx), _ptr(cy), k, _ptr(dist), _ptr(assign),
-                                   _stream(px))
+        dist = torch.empty((P, k), dtype=torch.float64, device=dev.device)
+        assign = torch.empty((P,), dtype=torch.int32, device=dev.device)
+        h = _native.handle(dev.device.index or 0)
+        rc = lib.gpm_kmeans_assign(h, _ptr(pxT), _ptr(pyT), P, n, _ptr(cx), _ptr(cy), k, _ptr(dist), _ptr(assign),
+                                   _stream(dev))
         _native.check(rc, "gpm_kmeans_assign")
         return assign.cpu().numpy(), dist.cpu().numpy()
 
-    def kmeansclustering(self, k, treshold=1000, plot=False, max_iter=1000, seed=None):
+    def kmeansclustering(self, k, treshold=1000, plot=False, max_iter=1000, seed=None, init=None):
         """Lloyd iterations with the reference's trajectory distance, stopping when the summed centroid
         shift drops below 5 (GPmap.py:90).  Returns {centroid_key: [path ids]}.
+
+        The paths are uploaded once; assignment, centroid means (members summed in path order, bit-exact with
+        ``calc_mean_traj``) and the convergence sum run on the device, several iterations per host round trip;
+        only the final assignment and centroids come back.
 
         Differences from the reference, all bug fixes: initial centroids closer than ``treshold`` are
         actually re-drawn (bounded retries; the reference's loop never terminates, GPmap.py:39-53); an
         empty cluster keeps its previous centroid (the reference raises ZeroDivisionError, GPmap.py:111);
-        plotting is opt-in."""
+        plotting is opt-in.  ``init`` (k path ids) fixes the initial centroids instead of drawing them."""
+        torch = _torch()
+        lib = _native.load()
         rng = rdm.Random(seed) if seed is not None else rdm
         keys = list(self.pathdict.keys())
         if k > len(keys):
             raise ValueError("more clusters than trajectories")
-        chosen = rng.sample(keys, k)
-        for _ in range(100):
+        chosen = list(init) if init is not None else rng.sample(keys, k)
+        if len(chosen) != k:
+            raise ValueError("init must name k paths")
+        for _ in range(0 if init is not None else 100):
             close = [(i, j) for i in range(k) for j in range(i + 1, k)
                      if self.calc_distance(self.pathdict[chosen[i]], self.pathdict[chosen[j]]) < treshold]
             free = [key for key in keys if key not in chosen]
@@ -444,25 +542,41 @@ class trajectories:
             name = "".join(rng.choices(string.ascii_uppercase + string.digits, k=5))
             if name not in names:
                 names.append(name)
-        cents = []
-        for key in chosen:
-            c = trajectory()
-            src = self.pathdict[key]
-            c.xs, c.ys, c.timestamp = src.xs.copy(), src.ys.copy(), src.timestamp.copy()
-            cents.append(c)
-        clusters = {}
-        for _ in range(max_iter):
-            assign, _d = self._assign(keys, cents)
-            clusters = {name: [] for name in names}
-            for key, a in zip(keys, assign):
-                clusters[names[int(a)]].append(key)
-            new = [self.calc_mean_traj(clusters[name]) if clusters[name] else cents[i]
-                   for i, name in enumerate(names)]
-            shift = sum(self.calc_distance(new[i], cents[i]) for i in range(k))
-            cents = new
-            if shift < 5:
+        dev, pxT, pyT = self._upload_paths(keys)                       # the one H2D copy of the call
+        _, P, n = dev.shape
+        index = {key: i for i, key in enumerate(keys)}
+        sel = torch.tensor([index[key] for key in chosen], dtype=torch.long, device=dev.device)
+        cents = dev[:, sel, :].contiguous()                           # (3, k, n): initial centroids = chosen paths
+        assign = torch.zeros((P,), dtype=torch.int32, device=dev.device)
+        ws = torch.empty(int(lib.gpm_kmeans_workspace_bytes(P, n, k)) // 8, dtype=torch.float64, device=dev.device)
+        h = _native.handle(dev.device.index or 0)
+        st = _stream(dev)
+        batch = 8                                                      # iterations enqueued per host round trip
+        iters, conv, shift = C.c_int32(0), C.c_int32(0), C.c_double(0.0)
+        done = 0
+        while done < max_iter:
+            todo = min(batch, max_iter - done)
+            todo += todo & 1                                           # even counts keep the ping-pong parity simple
+            rc = lib.gpm_kmeans_lloyd(h, _ptr(dev[0]), _ptr(dev[1]), _ptr(dev[2]), _ptr(pxT), _ptr(pyT), P, n, k,
+                                      _ptr(cents), _ptr(assign), 5.0, todo, 1 if done == 0 else 0, _ptr(ws), st)
+            _native.check(rc, "gpm_kmeans_lloyd")
+            _native.check(lib.gpm_kmeans_state(h, _ptr(ws), n, k, C.byref(iters), C.byref(conv), C.byref(shift), st),
+                          "gpm_kmeans_state")
+            done += todo
+            if conv.value:
                 break
-        self.centroids = dict(zip(names, cents))
+        final = ws[: 3 * k * n].view(3, k, n) if (iters.value & 1) else cents
+        final = final.cpu().numpy()
+        assign_h = assign.cpu().numpy()
+        self.kmeans_iterations, self.kmeans_shift = int(iters.value), float(shift.value)
+        clusters = {name: [] for name in names}
+        for key, a in zip(keys, assign_h):
+            clusters[names[int(a)]].append(key)
+        self.centroids = {}
+        for i, name in enumerate(names):
+            c = trajectory()
+            c.xs, c.ys, c.timestamp = final[0, i].copy(), final[1, i].copy(), final[2, i].copy()
+            self.centroids[name] = c
         if plot:
             self.plotclusters(clusters)
         return clusters

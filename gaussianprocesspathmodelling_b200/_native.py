@@ -30,6 +30,8 @@ SIGNATURES = {
     "gpm_destroy": (C.c_int, [_vp]),
     "gpm_sm_count": (C.c_int, [_vp]),
     "gpm_launch_count": (C.c_longlong, []),
+    "gpm_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "gpm_get_option": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int)]),
     "gpm_cov": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double), _vp, _i64, _i32, _vp]),
     "gpm_cross_cov": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double), _vp, C.POINTER(GpmGrid), _i64, _i64,
                                 _vp, _i64, _vp]),
@@ -39,12 +41,16 @@ SIGNATURES = {
     "gpm_predict_workspace_bytes": (_sz, [_vp, _i64, _i64]),
     "gpm_predict": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double), _vp, _i64, _vp, _vp, _i32,
                               _vp, C.POINTER(GpmGrid), _i64, _i64, _vp, _vp, _vp, _sz, _i32, _vp]),
-    "gpm_fit_batched_workspace_bytes": (_sz, [_i64, _i64]),
+    "gpm_fit_batched_workspace_bytes": (_sz, [_vp, _i64, _i64]),
     "gpm_fit_batched": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, C.POINTER(C.c_double), _i64,
                                   _vp, _vp, _vp, _vp, _vp]),
     "gpm_lml_grad_workspace_bytes": (_sz, [_i64]),
     "gpm_lml_grad": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double), _vp, _i64, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "gpm_kmeans_assign": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "gpm_kmeans_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "gpm_kmeans_lloyd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, C.c_double, _i32, _i32,
+                                   _vp, _vp]),
+    "gpm_kmeans_state": (C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(C.c_double), _vp]),
 }
 
 _lib = None
@@ -79,19 +85,70 @@ def check(rc, what):
         raise GpmError(f"{what} failed with code {rc}: {msg}")
 
 
-_handles = {}
+_handles = {}          # (device index, stream id) -> handle
+_options = {}          # option name -> value, applied to every handle (existing and future)
+_MAX_HANDLES = 64
 
 
-def handle(device_index: int):
-    """Per-device library handle (helper stream + events), created on first use."""
-    h = _handles.get(device_index)
+def handle(device_index: int, stream: int | None = None):
+    """Library handle for (device, CUDA stream), created on first use.
+
+    A handle is single-stream state (helper stream, events, the flags of the chained solves), so work issued on
+    different streams -- possibly from different Python threads -- gets different handles and cannot race.
+    ``stream`` defaults to torch's current stream on that device."""
+    device_index = int(device_index)
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream(device_index).cuda_stream
+    key = (device_index, int(stream))
+    h = _handles.get(key)
     if h is None:
         lib = load()
+        if len(_handles) >= _MAX_HANDLES:            # streams come and go: drop the oldest non-default-stream handle
+            for old in list(_handles):
+                if old[1] != 0:
+                    lib.gpm_destroy(_handles.pop(old))
+                    break
         hv = _vp()
-        check(lib.gpm_create(C.byref(hv), int(device_index)), "gpm_create")
+        check(lib.gpm_create(C.byref(hv), device_index), "gpm_create")
+        for name, value in _options.items():
+            check(lib.gpm_set_option(hv, name.encode(), int(value)), f"gpm_set_option({name})")
         h = hv
-        _handles[device_index] = h
+        _handles[key] = h
     return h
+
+
+def set_option(name: str, value: int):
+    """Set a debug / comparison switch (see gpm_set_option in include/gpmap_b200.h) on every handle."""
+    lib = load()
+    _options[name] = int(value)
+    for h in _handles.values():
+        check(lib.gpm_set_option(h, name.encode(), int(value)), f"gpm_set_option({name})")
+
+
+def get_option(name: str, device_index: int = 0) -> int:
+    v = C.c_int(0)
+    check(load().gpm_get_option(handle(device_index), name.encode(), C.byref(v)), f"gpm_get_option({name})")
+    return v.value
+
+
+class option:
+    """Context manager: ``with _native.option("no_lookahead", 1): ...`` (restores the previous value)."""
+
+    def __init__(self, name, value):
+        self.name, self.value = name, int(value)
+
+    def __enter__(self):
+        self.prev = _options.get(self.name)
+        self.prev_val = get_option(self.name) if self.prev is None else self.prev
+        set_option(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        set_option(self.name, self.prev_val)
+        if self.prev is None:
+            _options.pop(self.name, None)
+        return False
 
 
 def theta_array(theta):

@@ -1,6 +1,8 @@
 // Handle, error text and TMA tensor-map construction for libgpmap_b200.
 #include <atomic>
 #include <stdarg.h>
+#include <ctype.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -46,6 +48,30 @@ int make_tmap(gpm_handle_impl* h, CUtensorMap* map, const double* base, int64_t 
   return 0;
 }
 
+// name -> member table of the switches (gpm_set_option / gpm_get_option; GPM_<NAME> in the environment at gpm_create)
+struct OptEntry { const char* name; int Options::*member; };
+static const OptEntry kOptions[] = {
+    {"no_lookahead", &Options::no_lookahead},     {"tpc_wide", &Options::tpc_wide},
+    {"tpc_narrow", &Options::tpc_narrow},         {"wide_min", &Options::wide_min},
+    {"wide4_min", &Options::wide4_min},           {"wide8_min", &Options::wide8_min},
+    {"no_separable", &Options::no_separable},     {"no_small_fused", &Options::no_small_fused},
+    {"no_small_tiles", &Options::no_small_tiles}, {"no_fused_fwd", &Options::no_fused_fwd},
+    {"no_fused_mean", &Options::no_fused_mean},   {"var_steps", &Options::var_steps},
+    {"solve_steps", &Options::solve_steps},       {"grad_sweep", &Options::grad_sweep},
+    {"no_path_fused", &Options::no_path_fused},   {"no_fused_solve", &Options::no_fused_solve},
+};
+
+static void options_from_env(Options* o) {
+  for (const OptEntry& e : kOptions) {
+    char env[64] = "GPM_";
+    size_t n = 4;
+    for (const char* c = e.name; *c && n + 1 < sizeof(env); c++) env[n++] = (char)toupper((unsigned char)*c);
+    env[n] = 0;
+    const char* v = getenv(env);
+    if (v && *v) o->*(e.member) = atoi(v);
+  }
+}
+
 }  // namespace gpm
 
 using namespace gpm;
@@ -54,33 +80,45 @@ extern "C" {
 
 int gpm_version(void) { return GPM_VERSION; }
 
+int gpm_set_option(gpm_handle_t handle, const char* name, int value) {
+  GPM_ARG(handle != nullptr, 1);
+  GPM_ARG(name != nullptr, 2);
+  gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
+  for (const OptEntry& e : kOptions)
+    if (strcmp(e.name, name) == 0) { h->opt.*(e.member) = value; return 0; }
+  set_error("unknown option '%s'", name);
+  return -2;
+}
+
+int gpm_get_option(gpm_handle_t handle, const char* name, int* value) {
+  GPM_ARG(handle != nullptr, 1);
+  GPM_ARG(name != nullptr, 2);
+  GPM_ARG(value != nullptr, 3);
+  gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
+  for (const OptEntry& e : kOptions)
+    if (strcmp(e.name, name) == 0) { *value = h->opt.*(e.member); return 0; }
+  set_error("unknown option '%s'", name);
+  return -2;
+}
+
 long long gpm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* gpm_last_error(void) { return g_err; }
 
-int gpm_create(gpm_handle_t* handle, int device) {
-  GPM_ARG(handle != nullptr, 1);
-  *handle = nullptr;
-  int count = 0;
-  GPM_CUDA(cudaGetDeviceCount(&count));
-  GPM_ARG(device >= 0 && device < count, 2);
-  GPM_CUDA(cudaSetDevice(device));
+static int create_impl(gpm_handle_impl* h, int device) {
   cudaDeviceProp prop;
   GPM_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) {
     set_error("libgpmap_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
     return (int)cudaErrorNoKernelImageForDevice;
   }
-  gpm_handle_impl* h = new gpm_handle_impl();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
-  h->ev = nullptr;
-  h->n_ev = 0;
+  options_from_env(&h->opt);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
-    delete h;
     set_error("cuTensorMapEncodeTiled entry point not available");
     return e != cudaSuccess ? (int)e : 999;
   }
@@ -88,25 +126,51 @@ int gpm_create(gpm_handle_t* handle, int device) {
   int lo = 0, hi = 0;
   GPM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   GPM_CUDA(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi));
-  h->n_ev = 4;
-  h->ev = new cudaEvent_t[h->n_ev];
-  for (int i = 0; i < h->n_ev; i++) GPM_CUDA(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+  h->ev = new cudaEvent_t[4];
+  for (int i = 0; i < 4; i++) {
+    GPM_CUDA(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+    h->n_ev = i + 1;
+  }
   h->n_flags = 8192;                  // up to N = 2^20
   GPM_CUDA(cudaMalloc(&h->flags, 2 * h->n_flags * sizeof(int)));
   GPM_CUDA(cudaMemset(h->flags, 0, 2 * h->n_flags * sizeof(int)));
-  *handle = reinterpret_cast<gpm_handle_t>(h);
   return 0;
+}
+
+static void destroy_impl(gpm_handle_impl* h) {
+  for (int i = 0; i < h->n_ev; i++) cudaEventDestroy(h->ev[i]);
+  delete[] h->ev;
+  if (h->aux) cudaStreamDestroy(h->aux);
+  if (h->flags) cudaFree(h->flags);
+  delete h;
+}
+
+// A handle is SINGLE-STREAM and SINGLE-THREAD state: its helper stream, event pool and the flag arrays of the
+// chained solves are reused by every call, so calls that may overlap in time (other streams, other host threads)
+// need handles of their own.  The caller's current device is left as it was.
+int gpm_create(gpm_handle_t* handle, int device) {
+  GPM_ARG(handle != nullptr, 1);
+  *handle = nullptr;
+  int count = 0;
+  GPM_CUDA(cudaGetDeviceCount(&count));
+  GPM_ARG(device >= 0 && device < count, 2);
+  int prev = -1;
+  GPM_CUDA(cudaGetDevice(&prev));
+  GPM_CUDA(cudaSetDevice(device));
+  gpm_handle_impl* h = new gpm_handle_impl();
+  h->ev = nullptr; h->n_ev = 0; h->aux = nullptr; h->flags = nullptr;
+  const int rc = create_impl(h, device);
+  if (rc) destroy_impl(h);
+  else *handle = reinterpret_cast<gpm_handle_t>(h);
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  return rc;
 }
 
 int gpm_destroy(gpm_handle_t handle) {
   if (!handle) return 0;
   gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
-  cudaSetDevice(h->device);
-  for (int i = 0; i < h->n_ev; i++) cudaEventDestroy(h->ev[i]);
-  delete[] h->ev;
-  cudaStreamDestroy(h->aux);
-  cudaFree(h->flags);
-  delete h;
+  DeviceGuard guard(h->device);
+  destroy_impl(h);
   return 0;
 }
 

@@ -34,9 +34,10 @@ static inline long long round_up_ll(long long a, long long b) { return (a + b - 
 
 using namespace gpm;
 
-extern "C" size_t gpm_fit_batched_workspace_bytes(int64_t B, int64_t N) {
-  if (B <= 0 || N <= 0) return 0;
-  if (fit_small_supported(N)) return (size_t)B * 8 * sizeof(double);       // one CTA per path: only per-path theta is staged
+extern "C" size_t gpm_fit_batched_workspace_bytes(gpm_handle_t handle, int64_t B, int64_t N) {
+  if (!handle || B <= 0 || N <= 0) return 0;
+  const gpm_handle_impl* h = reinterpret_cast<const gpm_handle_impl*>(handle);
+  if (fit_small_supported(N) && !h->opt.no_small_fused) return (size_t)B * 8 * sizeof(double);       // one CTA per path: only per-path theta is staged
   const long long np = round_up_ll(N, NB);
   return (size_t)B * (size_t)(np * np + np * NB + 8 + np * 8) * sizeof(double);   // + per-path theta + z = L^{-1} Y
 }
@@ -47,7 +48,9 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
   GPM_ARG(handle != nullptr, 1);
   GPM_ARG(Xb != nullptr, 2);
   GPM_ARG(Yb != nullptr, 3);
-  GPM_ARG(B > 0 && (B <= 65535 || (fit_small_supported(N) && B < (1ll << 31))), 4);   // gridDim.y / gridDim.x
+  gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
+  const bool small = fit_small_supported(N) && !h->opt.no_small_fused;
+  GPM_ARG(B > 0 && (B <= 65535 || (small && B < (1ll << 31))), 4);   // gridDim.y / gridDim.x
   GPM_ARG(N > 0 && B * ((N + NB - 1) / NB * NB) < (1ll << 31), 5);
   Theta th;
   GPM_ARG(R >= 1 && R <= 8, 7);
@@ -57,9 +60,9 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
   GPM_ARG(alpha != nullptr && alpha != Yb, 10);
   GPM_ARG(info != nullptr, 12);
   GPM_ARG(ws != nullptr && ((uintptr_t)ws & 15) == 0, 13);
-  gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
+  DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (fit_small_supported(N)) {
+  if (small) {
     // short paths (the reference's 33-sample trajectories): one CTA per path, the whole fit in shared memory
     const double* tdev = nullptr;
     if (theta_stride) {
@@ -83,7 +86,7 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
   // Paths short enough for the one-CTA-per-path solve: the forward substitution rides along with the
   // factorisation (alpha holds the running residual, zf receives z = L^{-1} Y), and the solve kernel only
   // runs the backward pass.
-  if (solve_paths_supported(N) && getenv("GPM_NO_FUSED_FWD") == nullptr) {
+  if (solve_paths_supported(N) && !h->opt.no_fused_fwd) {
     double* zf = invD + (long long)B * nblk * NB * NB + (long long)B * 8;
     GPM_CUDA(cudaMemcpyAsync(alpha, Yb, (size_t)B * N * R * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if ((rc = potrf_blocked(h, Kb, N, np, invD, info, (int)B, np, st, alpha, zf, R, N))) return rc;

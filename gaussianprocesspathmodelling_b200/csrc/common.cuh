@@ -59,8 +59,27 @@ inline int make_theta(const double* theta, int D, Theta* out) {
   return 0;
 }
 
+// Debug / comparison switches.  Read ONCE from the environment (GPM_<NAME>) when the handle is created and
+// changed afterwards only through gpm_set_option(); the hot path never calls getenv().
+struct Options {
+  int no_lookahead = 0;      // potrf: no look-ahead stream
+  int tpc_wide = 4, tpc_narrow = 8;                    // potrf: tiles per CTA of the look-ahead updates
+  int wide_min = 32, wide4_min = 64, wide8_min = 96;   // potrf: outer panel width thresholds
+  int no_separable = 0;      // grid queries through the pointwise kernels
+  int no_small_fused = 0;    // short paths through the tiled pipeline
+  int no_small_tiles = 0;    // no latency tile kernel
+  int no_fused_fwd = 0;      // batched fits: separate forward substitution
+  int no_fused_mean = 0;     // predict: separate mean kernel
+  int var_steps = 0;         // variance: one launch per block column
+  int solve_steps = 0;       // solves: one launch per block step
+  int grad_sweep = 0;        // gradient: inverse by a triangular sweep
+  int no_path_fused = 0;     // batched fits of 112 < N <= 1024: the tiled batched pipeline instead of one CTA per path
+  int no_fused_solve = 0;    // single-matrix fit: separate forward substitution
+};
+
 struct gpm_handle_impl {
   int device;
+  Options opt;
   int sm_count;
   cudaStream_t aux;                 // high-priority helper stream for the look-ahead panel
   cudaEvent_t* ev;                  // event pool (cudaEventDisableTiming)
@@ -68,7 +87,19 @@ struct gpm_handle_impl {
   PFN_cuTensorMapEncodeTiled_v12000 encode;
   int* flags;                       // 2 x n_flags device ints: block-published flags of the chained solves
   int n_flags;                      //   (cleared on the stream at the start of every solve: graph-replay safe)
-  bool gemm_attr, potf2_attr, gemm_small_attr;       // opt-in shared-memory sizes set for this handle's device (function attributes are per device)
+  bool gemm_attr, potf2_attr, gemm_small_attr, gemm_strip_attr;       // opt-in shared-memory sizes set for this handle's device (function attributes are per device)
+};
+
+// Entry points run on the handle's device whatever the caller's current device is, and restore it on return.
+struct DeviceGuard {
+  int prev = -1, dev;
+  explicit DeviceGuard(int device) : dev(device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
 // 2-D row-major float64 tensor map with a [rows_box x 16] box and 128-byte swizzle.

@@ -369,8 +369,8 @@ predict_mean_grid_kernel(const double* __restrict__ X, long long N, Theta th, co
 }
 
 // separable grid kernels are used for grid queries unless GPM_NO_SEPARABLE is set (debugging / comparison)
-bool grid_separable_enabled(const gpm_grid_t* grid, long long m0, long long M) {
-  if (!grid || M <= 0 || grid->gx <= 0 || getenv("GPM_NO_SEPARABLE") != nullptr) return false;
+bool grid_separable_enabled(const gpm_handle_impl* h, const gpm_grid_t* grid, long long m0, long long M) {
+  if (!grid || M <= 0 || grid->gx <= 0 || h->opt.no_separable) return false;
   const long long rows = (m0 + M - 1) / grid->gx - m0 / grid->gx + 1;
   return (rows + 7) / 8 <= 65535;        // gridDim.y
 }
@@ -386,14 +386,14 @@ int launch_cov(const double* X, long long N, int D, const Theta& th, double* K, 
   return 0;
 }
 
-int launch_cross_cov_t(const double* X, long long N, int D, const Theta& th, const double* Xs,
+int launch_cross_cov_t(const gpm_handle_impl* h, const double* X, long long N, int D, const Theta& th, const double* Xs,
                        const gpm_grid_t* grid, long long m0, long long M, double* KsT, long long ldks,
                        long long ncols_pad, cudaStream_t stream) {
   if (M <= 0) return 0;
   gpm_grid_t g = {};
   if (grid) g = *grid;
   const int use_grid = Xs == nullptr;
-  if (use_grid && grid_separable_enabled(grid, m0, M)) {
+  if (use_grid && grid_separable_enabled(h, grid, m0, M)) {
     const long long row_first = m0 / g.gx, rows = (m0 + M - 1) / g.gx - row_first + 1;
     const int cols_per_cta = 1024;
     dim3 gd((unsigned)((g.gx + 7) / 8), (unsigned)((rows + 7) / 8), (unsigned)((ncols_pad + cols_per_cta - 1) / cols_per_cta));
@@ -435,10 +435,10 @@ int launch_cross_cov_mean(const double* X, long long N, int D, const Theta& th, 
 }
 
 template <int D>
-static int launch_mean_d(const double* X, long long N, const Theta& th, const double* alpha, int R,
+static int launch_mean_d(const gpm_handle_impl* h, const double* X, long long N, const Theta& th, const double* alpha, int R,
                          const double* Xs, const gpm_grid_t& g, int use_grid, long long m0, long long M,
                          double* mu, cudaStream_t stream) {
-  if (use_grid && grid_separable_enabled(&g, m0, M)) {
+  if (use_grid && grid_separable_enabled(h, &g, m0, M)) {
     const long long row_first = m0 / g.gx, rows = (m0 + M - 1) / g.gx - row_first + 1;
     dim3 gd((unsigned)((g.gx + 15) / 16), (unsigned)((rows + 15) / 16));
     if (R <= 1) predict_mean_grid_kernel<D, 1><<<gd, 256, 0, stream>>>(X, N, th, alpha, R, g, m0, M, row_first, mu);
@@ -457,15 +457,15 @@ static int launch_mean_d(const double* X, long long N, const Theta& th, const do
   return 0;
 }
 
-int launch_predict_mean(const double* X, long long N, int D, const Theta& th, const double* alpha, int R,
+int launch_predict_mean(const gpm_handle_impl* h, const double* X, long long N, int D, const Theta& th, const double* alpha, int R,
                         const double* Xs, const gpm_grid_t* grid, long long m0, long long M, double* mu,
                         cudaStream_t stream) {
   if (M <= 0) return 0;
   gpm_grid_t g = {};
   if (grid) g = *grid;
   const int use_grid = Xs == nullptr;
-  return D == 2 ? launch_mean_d<2>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, mu, stream)
-                : launch_mean_d<3>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, mu, stream);
+  return D == 2 ? launch_mean_d<2>(h, X, N, th, alpha, R, Xs, g, use_grid, m0, M, mu, stream)
+                : launch_mean_d<3>(h, X, N, th, alpha, R, Xs, g, use_grid, m0, M, mu, stream);
 }
 
 }  // namespace gpm
@@ -481,6 +481,7 @@ extern "C" int gpm_cov(gpm_handle_t h, const double* X, int64_t N, int32_t D, co
   GPM_ARG(make_theta(theta, D, &th) == 0, 5);
   GPM_ARG(K != nullptr && ((uintptr_t)K & 15) == 0, 6);
   GPM_ARG(ldk >= N && (ldk & 1) == 0, 7);
+  DeviceGuard guard(reinterpret_cast<gpm_handle_impl*>(h)->device);
   return launch_cov(X, N, D, th, K, ldk, (flags & GPM_COV_LOWER) ? 1 : 0, 1, 0, 0, (cudaStream_t)stream, nullptr, 0);
 }
 
@@ -496,5 +497,11 @@ extern "C" int gpm_cross_cov(gpm_handle_t h, const double* X, int64_t N, int32_t
   GPM_ARG(m0 >= 0 && m1 >= m0, 8);
   GPM_ARG(KsT != nullptr, 10);
   GPM_ARG(ldks >= N, 11);
-  return launch_cross_cov_t(X, N, D, th, Xs, grid, m0, m1 - m0, KsT, ldks, N, (cudaStream_t)stream);
+  if (!Xs) {
+    GPM_ARG(grid->gx > 0 && grid->gy > 0, 7);
+    GPM_ARG(m1 <= (int64_t)grid->gx * grid->gy, 9);
+  }
+  gpm_handle_impl* hi = reinterpret_cast<gpm_handle_impl*>(h);
+  DeviceGuard guard(hi->device);
+  return launch_cross_cov_t(hi, X, N, D, th, Xs, grid, m0, m1 - m0, KsT, ldks, N, (cudaStream_t)stream);
 }

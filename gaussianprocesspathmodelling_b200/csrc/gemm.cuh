@@ -70,7 +70,7 @@ inline int gemm_grid_x(const GemmArgs& a) {
 }
 
 // mapC describes the matrix args.C points into (used to prefetch C tiles by TMA when epi == EPI_SUB)
-bool gemm_small_eligible(const GemmArgs& a, int batch);
+bool gemm_small_eligible(const gpm_handle_impl* h, const GemmArgs& a, int batch);
 int launch_gemm_small(gpm_handle_impl* h, const GemmArgs& a, cudaStream_t stream);
 
 int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& mapB,

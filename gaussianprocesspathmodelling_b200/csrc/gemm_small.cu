@@ -135,11 +135,116 @@ gemm_nt_small_kernel(const GemmArgs p) {
   }
 }
 
+
+// In-place variant (C region == A region: the panel solve L[i,k] = K[i,k] inv(L_kk)^T of the factorisation).  With
+// 64 x 64 quarters the quarter (qi, 1) would read the columns of A that quarter (qi, 0) overwrites, and nothing orders
+// two CTAs.  Here a tile is split into four STRIPS of 32 rows x 128 columns instead: a CTA reads only the rows of A it
+// writes, and every cp.async of its own has completed (and been consumed) before its first store.  Eight warps side
+// by side, warp tile 32 x 16 as in the quarter kernel, the same DMMA sequence per output element.
+constexpr int SR = 32;                   // strip rows
+constexpr int STRIP_SMEM = 2 /*stages*/ * (SR + NB) * PITCH * 8;
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+gemm_nt_strip_kernel(const GemmArgs p) {
+  extern __shared__ __align__(16) double smem_d[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t = blockIdx.x >> 2, strip = blockIdx.x & 3;
+  const int ti = t % p.tiles_m, tj = t / p.tiles_m;          // never triangular: a panel is one tile column
+  const long long a_row = (long long)p.a_row0 + ti * NB + strip * SR;
+  const long long b_row = (long long)p.b_row0 + tj * p.b_tile_rows;
+  const long long c_row = p.c_row0 + (long long)ti * NB + strip * SR;
+  const long long c_col = p.c_col0 + (long long)tj * NB;
+  if (c_row >= p.c_rows_end || c_col >= p.c_cols_end) return;
+  const int nchunk = p.klen / KC;
+  const int wn = warp, g = lane >> 2, q = lane & 3;
+  // a lower-triangular B block (inverted diagonal block, B[n][c] = 0 for c > n): slab s (16 deep) is all zero for
+  // this warp's columns [16 wn, 16 wn + 16) when s > wn
+  const int last_slab = p.tri_b ? wn : 1 << 30;
+
+  const long long a_rows_end = p.small_a_rows_end, b_rows_end = p.small_b_rows_end;
+  constexpr int STAGE = (SR + NB) * PITCH;
+  auto stage = [&](int chunk, int buf) {
+#pragma unroll
+    for (int u = 0; u < 5; u++) {
+      const int piece = tid + SMALL_THREADS * u;          // 0..1279: 256 pieces of A (32 rows), 1024 of B (128 rows)
+      const bool isb = piece >= SR * 8;
+      const int pp = isb ? piece - SR * 8 : piece;
+      const int r = pp >> 4, c16 = pp & 15;
+      const long long grow = isb ? min(b_row + r, b_rows_end - 1) : min(a_row + r, a_rows_end - 1);
+      const double* src = isb ? p.small_B + grow * p.small_ldb + p.b_col0 + chunk * KC + c16 * 2
+                              : p.small_A + grow * p.small_lda + p.a_col0 + chunk * KC + c16 * 2;
+      const uint32_t dst = smem_u32(smem_d + buf * STAGE + ((isb ? SR : 0) + r) * PITCH + c16 * 2);
+      cp_async16(dst, src);
+    }
+    cp_async_commit();
+  };
+
+  double acc[4][2][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+  if (nchunk > 0) stage(0, 0);
+  for (int c = 0; c < nchunk; c++) {
+    if (c + 1 < nchunk) { stage(c + 1, (c + 1) & 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const double* As = smem_d + (c & 1) * STAGE + g * PITCH;
+    const double* Bs = smem_d + (c & 1) * STAGE + (SR + wn * 16 + g) * PITCH;
+#pragma unroll
+    for (int s2 = 0; s2 < 2; s2++) {
+      if (2 * c + s2 > last_slab) continue;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; k4++) {
+        const int k = s2 * 16 + 2 * k4 + 8 * (q >> 1) + (q & 1);
+        double a[4], b[2];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) a[mt] = As[mt * 8 * PITCH + k];
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) b[nt] = Bs[nt * 8 * PITCH + k];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 2; nt++) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+      }
+    }
+    __syncthreads();                     // the buffer is overwritten by the stage after next
+  }
+  // every read of A by this CTA is complete (the last chunk was consumed before the barrier above); the stores
+  // below touch only the 32 rows this CTA read
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++) {
+    const long long row = c_row + mt * 8 + g;
+    if (row >= p.c_rows_end) continue;
+    double* crow = p.C + row * p.ldc;
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+      const long long col = c_col + wn * 16 + nt * 8 + 2 * q;
+      double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
+      if (p.epi == EPI_NEG) { v0 = -v0; v1 = -v1; }
+      if (col + 1 < p.c_cols_end) *reinterpret_cast<double2*>(crow + col) = make_double2(v0, v1);
+      else if (col < p.c_cols_end) crow[col] = v0;
+    }
+  }
+}
+
+// the output tile range overlaps the rows and columns the A operand is read from
+static bool gemm_small_inplace(const GemmArgs& a) {
+  if (a.C != a.small_A) return false;
+  const long long a_c0 = a.a_col0, a_c1 = a.a_col0 + a.klen;
+  const long long c_c0 = a.c_col0, c_c1 = a.c_col0 + (long long)(a.tri ? a.tiles_m : a.tiles_n) * NB;
+  return a_c0 < c_c1 && c_c0 < a_c1;      // column ranges intersect (the row ranges always do in the factorisation)
+}
+
 // true when `args` (tile mode, one matrix) is small enough for the latency kernel and carries raw operand pointers
-bool gemm_small_eligible(const GemmArgs& a, int batch) {
-  if (getenv("GPM_NO_SMALL_TILES") != nullptr || batch != 1 || a.small_A == nullptr || a.small_B == nullptr) return false;
+bool gemm_small_eligible(const gpm_handle_impl* h, const GemmArgs& a, int batch) {
+  if (h->opt.no_small_tiles || batch != 1 || a.small_A == nullptr || a.small_B == nullptr) return false;
   if (a.sweep_nblk > 0 || a.rowsq || a.rhs_r || a.kstart_mode || a.kend_mode || a.batch_cols) return false;
   if (a.klen % KC != 0 || (a.small_lda & 1) || (a.small_ldb & 1) || (a.a_col0 & 1) || (a.b_col0 & 1)) return false;
+  // in place (the output overwrites the A operand): only the strip kernel is safe, and it handles plain
+  // EPI_STORE / EPI_NEG tile columns
+  if (gemm_small_inplace(a) && (a.tri || a.epi == EPI_SUB)) return false;
   return gemm_grid_x(a) <= SMALL_MAX_TILES;
 }
 
@@ -147,6 +252,15 @@ int launch_gemm_small(gpm_handle_impl* h, const GemmArgs& a, cudaStream_t stream
   if (!h->gemm_small_attr) {
     GPM_CUDA(cudaFuncSetAttribute(gemm_nt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
     h->gemm_small_attr = true;
+  }
+  if (gemm_small_inplace(a)) {
+    if (!h->gemm_strip_attr) {
+      GPM_CUDA(cudaFuncSetAttribute(gemm_nt_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM));
+      h->gemm_strip_attr = true;
+    }
+    gemm_nt_strip_kernel<<<gemm_grid_x(a) * 4, SMALL_THREADS, STRIP_SMEM, stream>>>(a);
+    GPM_LAUNCH_CHECK();
+    return 0;
   }
   gemm_nt_small_kernel<<<gemm_grid_x(a) * 4, SMALL_THREADS, SMALL_SMEM, stream>>>(a);
   GPM_LAUNCH_CHECK();

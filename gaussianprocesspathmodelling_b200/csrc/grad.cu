@@ -165,6 +165,7 @@ extern "C" int gpm_lml_grad(gpm_handle_t handle, const double* X, int64_t N, int
   GPM_ARG(ws != nullptr && ((uintptr_t)ws & 15) == 0, 12);
   GPM_ARG(ws_bytes >= gpm_lml_grad_workspace_bytes(N), 13);
   gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
+  DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const long long np = round_up_g(N, NB);
   const int nblk = (int)(np / NB);
@@ -179,7 +180,7 @@ extern "C" int gpm_lml_grad(gpm_handle_t handle, const double* X, int64_t N, int
   if ((rc = make_tmap(h, &mapInv, reinterpret_cast<const double*>(potrf_ws), (long long)nblk * NB, NB, NB, NB))) return rc;
   if ((rc = make_tmap(h, &mapKi, Kinv, np, np, np, NB))) return rc;
 
-  if (getenv("GPM_GRAD_SWEEP")) {
+  if (h->opt.grad_sweep) {
     // reference path: W = I, then W <- W L^{-T} by the triangular sweep (row block 0 is a long serial chain)
     dim3 gi((unsigned)np, (unsigned)((np + 255) / 256));
     identity_kernel<<<gi, 256, 0, st>>>(W, N, np, np);

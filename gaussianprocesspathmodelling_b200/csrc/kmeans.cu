@@ -1,15 +1,33 @@
-// SURVEY.md section 8f "next" #1: the reference's real hot loop, trajectories.calc_distance inside
-// kmeansclustering (GPmap.py:72-80, 114-121).  dist[p,c] = sum_i hypot-free sqrt(dx^2+dy^2) summed
-// sequentially in sample order (as the reference's Python float accumulation does), and the
-// first-minimum assignment with strict '<' (GPmap.py:76).  One thread per (path, centroid) pair.
+// SURVEY.md section 8f "next" #1: the reference's real hot loop, trajectories.kmeansclustering (GPmap.py:36-93), as a
+// kernel pair that keeps the whole Lloyd iteration on the device:
+//
+//   assign  (GPmap.py:72-80, 114-121)  dist[p,c] = sum_i sqrt(dx^2 + dy^2), summed sequentially in sample order as the
+//                                      reference's Python float accumulation does; first minimum with strict '<'.
+//   update  (GPmap.py:83-84, 95-112)   centroid c = point-wise mean of its members' xs, ys, timestamp, the members
+//                                      summed in path order (the order the reference appends them to the cluster
+//                                      list), then divided by the member count: bit-exact with calc_mean_traj.
+//   finish  (GPmap.py:87-90)           shift = sum_c calc_distance(new_c, old_c);  converged when shift < threshold.
+//
+// The paths are uploaded once per clustering call in two layouts: sample-major [n][P] for the assignment (one
+// thread per path: a warp's loads are 256 contiguous bytes) and path-major [P][n] for the update (one thread per
+// sample: same).  Every kernel of an iteration returns at once when the device-side `converged` flag is set, so
+// the host can enqueue several iterations back to back and look at the 16-byte state only once per batch.
 #include "common.cuh"
 
 namespace gpm {
 
+struct KmState {          // device-resident state of a clustering call
+  int iters;              // finished Lloyd iterations
+  int converged;          // set by the finish kernel when shift < threshold
+  double shift;           // summed centroid shift of the last finished iteration
+};
+
+// pxT, pyT: [n][P].  cx, cy: [k][n].  One thread per path; centroids staged in shared memory.
 __global__ void __launch_bounds__(128)
-kmeans_assign_kernel(const double* __restrict__ px, const double* __restrict__ py, long long P, int n,
+kmeans_assign_kernel(const double* __restrict__ pxT, const double* __restrict__ pyT, long long P, int n,
                      const double* __restrict__ cx, const double* __restrict__ cy, int k,
-                     double* __restrict__ dist, int* __restrict__ assign) {
+                     double* __restrict__ dist, int* __restrict__ assign, const KmState* __restrict__ state) {
+  if (state && state->converged) return;
   extern __shared__ double sc[];          // centroids: cx[k][n] then cy[k][n]
   for (int e = threadIdx.x; e < k * n; e += blockDim.x) { sc[e] = cx[e]; sc[k * n + e] = cy[e]; }
   __syncthreads();
@@ -18,37 +36,183 @@ kmeans_assign_kernel(const double* __restrict__ px, const double* __restrict__ p
   double best = 0.0;
   int best_c = 0;
   for (int c = 0; c < k; c++) {
+    const double* ccx = sc + c * n;
+    const double* ccy = sc + k * n + c * n;
     double s = 0.0;
+#pragma unroll 4
     for (int i = 0; i < n; i++) {
-      const double dx = px[p * n + i] - sc[c * n + i];
-      const double dy = py[p * n + i] - sc[k * n + c * n + i];
+      const double dx = pxT[(long long)i * P + p] - ccx[i];
+      const double dy = pyT[(long long)i * P + p] - ccy[i];
       s = __dadd_rn(s, sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
     }
     if (dist) dist[p * k + c] = s;
     if (c == 0 || s < best) { best = s; best_c = c; }
   }
-  if (assign) assign[p] = best_c;
+  assign[p] = best_c;
+}
+
+// One CTA per centroid; thread (a, i) owns sample i of array a in {xs, ys, timestamp}.  px, py, pt: [P][n].
+// cold / cnew: [3][k][n] (xs, ys, timestamp planes).  An empty cluster keeps its previous centroid.
+__global__ void __launch_bounds__(256)
+kmeans_update_kernel(const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pt,
+                     long long P, int n, int k, const int* __restrict__ assign, const double* __restrict__ cold,
+                     double* __restrict__ cnew, double* __restrict__ shift_c, const KmState* __restrict__ state) {
+  if (state->converged) return;
+  constexpr int CH = 1024;
+  __shared__ int members[CH];
+  __shared__ int nmem;
+  __shared__ long long total;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const int work = 3 * n;
+  if (tid == 0) total = 0;
+  // each thread carries up to SLOTS running sums (sample slots tid, tid + 256, ...)
+  constexpr int SLOTS = 8;                 // 3 n <= 2048
+  double sum[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; s++) sum[s] = 0.0;
+  for (long long p0 = 0; p0 < P; p0 += CH) {
+    __syncthreads();
+    if (tid < 32) {                        // warp 0: ordered compaction of this chunk's members (path order = sum order)
+      int m = 0;
+      const int lim = (int)((P - p0) < CH ? (P - p0) : CH);
+      for (int j0 = 0; j0 < lim; j0 += 32) {
+        const int j = j0 + tid;
+        const bool is = j < lim && assign[p0 + j] == c;
+        const unsigned mask = __ballot_sync(0xffffffffu, is);
+        if (is) members[m + __popc(mask & ((1u << tid) - 1u))] = j;
+        m += __popc(mask);
+      }
+      if (tid == 0) { nmem = m; total += m; }
+    }
+    __syncthreads();
+    const int m = nmem;
+#pragma unroll
+    for (int s = 0; s < SLOTS; s++) {
+      const int w = tid + 256 * s;
+      if (w >= work) break;
+      const int a = w / n, i = w - a * n;
+      const double* src = (a == 0 ? px : (a == 1 ? py : pt)) + p0 * n + i;
+      double acc = sum[s];
+      for (int j = 0; j < m; j++) acc = __dadd_rn(acc, src[(long long)members[j] * n]);
+      sum[s] = acc;
+    }
+  }
+  __syncthreads();
+  const long long cnt = total;
+#pragma unroll
+  for (int s = 0; s < SLOTS; s++) {
+    const int w = tid + 256 * s;
+    if (w >= work) break;
+    const int a = w / n, i = w - a * n;
+    const long long off = ((long long)a * k + c) * n + i;
+    cnew[off] = cnt > 0 ? sum[s] / (double)cnt : cold[off];
+  }
+  __syncthreads();
+  if (tid == 0) {                          // calc_distance(new_c, old_c): sequential, as the reference
+    double s = 0.0;
+    for (int i = 0; i < n; i++) {
+      const double dx = cnew[(long long)c * n + i] - cold[(long long)c * n + i];
+      const double dy = cnew[((long long)k + c) * n + i] - cold[((long long)k + c) * n + i];
+      s = __dadd_rn(s, sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+    }
+    shift_c[c] = s;
+  }
+}
+
+__global__ void kmeans_finish_kernel(const double* __restrict__ shift_c, int k, double threshold, KmState* state) {
+  if (threadIdx.x != 0 || state->converged) return;
+  double s = 0.0;
+  for (int c = 0; c < k; c++) s = __dadd_rn(s, shift_c[c]);
+  state->shift = s;
+  state->iters += 1;
+  if (s < threshold) state->converged = 1;
 }
 
 }  // namespace gpm
 
 using namespace gpm;
 
-extern "C" int gpm_kmeans_assign(gpm_handle_t h, const double* px, const double* py, int64_t P, int32_t n,
+extern "C" int gpm_kmeans_assign(gpm_handle_t h, const double* pxT, const double* pyT, int64_t P, int32_t n,
                                  const double* cx, const double* cy, int32_t k, double* dist,
                                  int32_t* assign, gpm_stream_t stream) {
   GPM_ARG(h != nullptr, 1);
-  GPM_ARG(px != nullptr, 2);
-  GPM_ARG(py != nullptr, 3);
+  GPM_ARG(pxT != nullptr, 2);
+  GPM_ARG(pyT != nullptr, 3);
   GPM_ARG(P > 0, 4);
   GPM_ARG(n > 0, 5);
   GPM_ARG(cx != nullptr, 6);
   GPM_ARG(cy != nullptr, 7);
   GPM_ARG(k > 0 && (size_t)k * n * 16 <= 200 * 1024, 8);
+  GPM_ARG(assign != nullptr, 10);
+  DeviceGuard guard(reinterpret_cast<gpm_handle_impl*>(h)->device);
   const size_t smem = (size_t)k * n * 16;
   if (smem > 48 * 1024)
     GPM_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kmeans_assign_kernel<<<(unsigned)((P + 127) / 128), 128, smem, (cudaStream_t)stream>>>(px, py, P, n, cx, cy, k, dist, assign);
+  kmeans_assign_kernel<<<(unsigned)((P + 127) / 128), 128, smem, (cudaStream_t)stream>>>(pxT, pyT, P, n, cx, cy, k, dist, assign, nullptr);
   GPM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t gpm_kmeans_workspace_bytes(int64_t P, int32_t n, int32_t k) {
+  if (P <= 0 || n <= 0 || k <= 0) return 0;
+  // second centroid buffer [3][k][n] + per-centroid shifts [k] + state
+  return ((size_t)3 * k * n + (size_t)k + 2) * sizeof(double);
+}
+
+extern "C" int gpm_kmeans_lloyd(gpm_handle_t h, const double* px, const double* py, const double* pt,
+                                const double* pxT, const double* pyT, int64_t P, int32_t n, int32_t k,
+                                double* centroids, int32_t* assign, double threshold, int32_t iters,
+                                int32_t first, void* ws, gpm_stream_t stream) {
+  GPM_ARG(h != nullptr, 1);
+  GPM_ARG(px != nullptr && py != nullptr && pt != nullptr, 2);
+  GPM_ARG(pxT != nullptr && pyT != nullptr, 5);
+  GPM_ARG(P > 0, 7);
+  GPM_ARG(n > 0 && 3 * n <= 2048, 8);
+  GPM_ARG(k > 0 && (size_t)k * n * 16 <= 200 * 1024, 9);
+  GPM_ARG(centroids != nullptr, 10);
+  GPM_ARG(assign != nullptr, 11);
+  GPM_ARG(iters >= 0, 13);
+  GPM_ARG(ws != nullptr && ((uintptr_t)ws & 7) == 0, 15);
+  DeviceGuard guard(reinterpret_cast<gpm_handle_impl*>(h)->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* buf1 = reinterpret_cast<double*>(ws);
+  double* shift_c = buf1 + (size_t)3 * k * n;
+  KmState* state = reinterpret_cast<KmState*>(shift_c + k);
+  if (first) GPM_CUDA(cudaMemsetAsync(state, 0, sizeof(KmState), st));
+  const size_t smem = (size_t)k * n * 16;
+  if (smem > 48 * 1024)
+    GPM_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t plane = (size_t)k * n;
+  // Iterations ping-pong between `centroids` (even) and the workspace buffer (odd).  Once `converged` is set every
+  // later kernel is a no-op, so state->iters tells the caller which buffer holds the final centroids; an even
+  // number of enqueued iterations per call keeps the parity bookkeeping on the caller's side trivial.
+  GPM_ARG((iters & 1) == 0, 13);
+  for (int it = 0; it < iters; it++) {
+    double* cur = (it & 1) ? buf1 : centroids;
+    double* nxt = (it & 1) ? centroids : buf1;
+    kmeans_assign_kernel<<<(unsigned)((P + 127) / 128), 128, smem, st>>>(pxT, pyT, P, n, cur, cur + plane, k, nullptr, assign, state);
+    GPM_LAUNCH_CHECK();
+    kmeans_update_kernel<<<k, 256, 0, st>>>(px, py, pt, P, n, k, assign, cur, nxt, shift_c, state);
+    GPM_LAUNCH_CHECK();
+    kmeans_finish_kernel<<<1, 32, 0, st>>>(shift_c, k, threshold, state);
+    GPM_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int gpm_kmeans_state(gpm_handle_t h, const void* ws, int32_t n, int32_t k, int32_t* iters,
+                                int32_t* converged, double* shift, gpm_stream_t stream) {
+  GPM_ARG(h != nullptr, 1);
+  GPM_ARG(ws != nullptr, 2);
+  GPM_ARG(n > 0 && k > 0, 3);
+  DeviceGuard guard(reinterpret_cast<gpm_handle_impl*>(h)->device);
+  const double* buf1 = reinterpret_cast<const double*>(ws);
+  const KmState* state = reinterpret_cast<const KmState*>(buf1 + (size_t)3 * k * n + k);
+  KmState hs;
+  GPM_CUDA(cudaMemcpyAsync(&hs, state, sizeof(KmState), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  GPM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (iters) *iters = hs.iters;
+  if (converged) *converged = hs.converged;
+  if (shift) *shift = hs.shift;
   return 0;
 }

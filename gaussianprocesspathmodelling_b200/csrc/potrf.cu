@@ -520,7 +520,7 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
   rc = make_tmap(h, &mapInv, invD, (long long)batch * nblk * NB, NB, NB, NB);
   if (rc) return rc;
   const long long batch_k = batch_rows * ldk, batch_inv = (long long)nblk * NB * NB;
-  const bool lookahead = getenv("GPM_NO_LOOKAHEAD") == nullptr && nblk > 2 && batch < 32;
+  const bool lookahead = !h->opt.no_lookahead && nblk > 2 && batch < 32;
   cudaStream_t s1 = lookahead ? h->aux : s0;
   rc = ensure_events(h, 2 * nblk + 2);
   if (rc) return rc;
@@ -572,8 +572,7 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
     }
     a.a_row0 = jlo * NB; a.b_row0 = jlo * NB;
     a.c_row0 = (long long)jlo * NB; a.c_col0 = (long long)jlo * NB;
-    static const int tpc_wide = getenv("GPM_TPC_WIDE") ? atoi(getenv("GPM_TPC_WIDE")) : 4;
-    static const int tpc_narrow = getenv("GPM_TPC_NARROW") ? atoi(getenv("GPM_TPC_NARROW")) : 8;
+    const int tpc_wide = h->opt.tpc_wide, tpc_narrow = h->opt.tpc_narrow;
     a.max_tiles_per_cta = lookahead ? (kw > 2 ? 2 : (kw > 1 ? tpc_wide : tpc_narrow)) : 16;   // keep CTAs short enough for the panel stream
     return launch_gemm(h, mapK, mapK, mapK, a, batch, st);
   };
@@ -594,9 +593,7 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
   // then 1 (thresholds swept on B200 at N = 8192 and 16384, tools/potrf_sweep.sh and potrf_sweep2.sh; the response
   // is flat within 1 % around these values).
   // Large batches are throughput-bound in every launch, so they use width 2 and no look-ahead.
-  static const int wide_env = getenv("GPM_WIDE_MIN") ? atoi(getenv("GPM_WIDE_MIN")) : 32;
-  static const int wide4_env = getenv("GPM_WIDE4_MIN") ? atoi(getenv("GPM_WIDE4_MIN")) : 64;
-  static const int wide8_env = getenv("GPM_WIDE8_MIN") ? atoi(getenv("GPM_WIDE8_MIN")) : 96;
+  const int wide_env = h->opt.wide_min, wide4_env = h->opt.wide4_min, wide8_env = h->opt.wide8_min;
   std::vector<int> pb(nblk + 1), pw(nblk + 1);
   int npanel = 0;
   for (int b = 0; b < nblk;) {
@@ -666,5 +663,6 @@ extern "C" int gpm_potrf(gpm_handle_t handle, double* K, int64_t N, int64_t ldk,
   GPM_ARG(ws != nullptr && ((uintptr_t)ws & 15) == 0, 5);
   GPM_ARG(info != nullptr, 6);
   gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
+  DeviceGuard guard(h->device);
   return potrf_blocked(h, K, N, ldk, reinterpret_cast<double*>(ws), info, 1, 0, (cudaStream_t)stream, nullptr, nullptr, 0, 0);
 }

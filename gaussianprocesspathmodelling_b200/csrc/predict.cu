@@ -13,21 +13,21 @@
 
 namespace gpm {
 
-int launch_cross_cov_t(const double* X, long long N, int D, const Theta& th, const double* Xs,
+int launch_cross_cov_t(const gpm_handle_impl* h, const double* X, long long N, int D, const Theta& th, const double* Xs,
                        const gpm_grid_t* grid, long long m0, long long M, double* KsT, long long ldks,
                        long long ncols_pad, cudaStream_t stream);
 int launch_cross_cov_mean(const double* X, long long N, int D, const Theta& th, const double* alpha, int R,
                           const double* Xs, const gpm_grid_t* grid, long long m0, long long M, double* KsT,
                           long long ldks, long long ncols_pad, double* mu, cudaStream_t stream);
-int launch_predict_mean(const double* X, long long N, int D, const Theta& th, const double* alpha, int R,
+int launch_predict_mean(const gpm_handle_impl* h, const double* X, long long N, int D, const Theta& th, const double* alpha, int R,
                         const double* Xs, const gpm_grid_t* grid, long long m0, long long M, double* mu,
                         cudaStream_t stream);
-bool grid_separable_enabled(const gpm_grid_t* grid, long long m0, long long M);
+bool grid_separable_enabled(const gpm_handle_impl* h, const gpm_grid_t* grid, long long m0, long long M);
 
 __global__ void var_finalize_kernel(const double* __restrict__ rowsq, long long M, double base,
                                     double* __restrict__ var) {
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m < M) var[m] = base - rowsq[m];
+  if (m < M) var[m] = fmax(base - rowsq[m], 0.0);      // cancellation next to training points can give -1e-16 * base
 }
 
 static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
@@ -70,6 +70,7 @@ extern "C" int gpm_predict(gpm_handle_t handle, const double* X, int64_t N, int3
   GPM_ARG(m0 >= 0 && m1 >= m0, 13);
   if (!Xs) GPM_ARG(m1 <= (int64_t)grid->gx * grid->gy, 14);
   gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
+  DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const long long M = m1 - m0;
   if (M == 0) return 0;
@@ -81,9 +82,9 @@ extern "C" int gpm_predict(gpm_handle_t handle, const double* X, int64_t N, int3
     GPM_ARG(mu != nullptr, 15);
     // with the variance requested and R <= 2 the mean is fused into the cross-covariance pass below
     // (grid queries: the separable mean kernel + the separable cross-covariance are cheaper than the fused pass)
-    fuse_mean = (flags & GPM_PREDICT_VAR) && R <= 2 && getenv("GPM_NO_FUSED_MEAN") == nullptr &&
-                !(Xs == nullptr && grid_separable_enabled(grid, m0, M));
-    if (!fuse_mean && (rc = launch_predict_mean(X, N, D, th, alpha, R, Xs, grid, m0, M, mu, st))) return rc;
+    fuse_mean = (flags & GPM_PREDICT_VAR) && R <= 2 && !h->opt.no_fused_mean &&
+                !(Xs == nullptr && grid_separable_enabled(h, grid, m0, M));
+    if (!fuse_mean && (rc = launch_predict_mean(h, X, N, D, th, alpha, R, Xs, grid, m0, M, mu, st))) return rc;
   }
   if (!(flags & GPM_PREDICT_VAR)) return 0;
   GPM_ARG(L != nullptr && ((uintptr_t)L & 15) == 0, 6);
@@ -110,9 +111,9 @@ extern "C" int gpm_predict(gpm_handle_t handle, const double* X, int64_t N, int3
     if (fuse_mean)
       rc = launch_cross_cov_mean(X, N, D, th, alpha, R, Xs, grid, m0 + c0, mc, W, npad, npad, mu + c0 * R, st);
     else
-      rc = launch_cross_cov_t(X, N, D, th, Xs, grid, m0 + c0, mc, W, npad, npad, st);
+      rc = launch_cross_cov_t(h, X, N, D, th, Xs, grid, m0 + c0, mc, W, npad, npad, st);
     if (rc) return rc;
-    const bool per_step = getenv("GPM_VAR_STEPS") != nullptr;        // debugging: one launch per block column
+    const bool per_step = h->opt.var_steps != 0;        // debugging: one launch per block column
     GemmArgs a = {};
     a.C = W; a.ldc = npad;
     a.tiles_m = tiles; a.tiles_n = 1; a.tri = 0;

@@ -154,9 +154,7 @@ fit_small_kernel(const double* __restrict__ Xb, const double* __restrict__ Yb, i
   }
 }
 
-bool fit_small_supported(long long N) {
-  return N >= 1 && N <= SMALL_MAX_N && getenv("GPM_NO_SMALL_FUSED") == nullptr;
-}
+bool fit_small_supported(long long N) { return N >= 1 && N <= SMALL_MAX_N; }
 
 static size_t small_smem(int N, int RR) {
   return (size_t)(tri(N) + 3 * N + 2 * N + N * RR + 4 * (RR + 1)) * sizeof(double);

@@ -536,15 +536,17 @@ extern "C" int gpm_solve_lml(gpm_handle_t h, const double* L, int64_t N, int64_t
   GPM_ARG(h != nullptr, 1);
   GPM_ARG(L != nullptr, 2);
   GPM_ARG(N > 0, 3);
-  GPM_ARG(ldl >= N, 4);
+  GPM_ARG(L != nullptr && ((uintptr_t)L & 15) == 0, 2);
+  GPM_ARG(ldl >= N && (ldl & 1) == 0, 4);
   GPM_ARG(potrf_ws != nullptr, 5);
   GPM_ARG(Y != nullptr, 6);
   GPM_ARG(R >= 1 && R <= RMAX, 7);
   GPM_ARG(alpha != nullptr && alpha != Y, 8);
   cudaStream_t st = (cudaStream_t)stream;
+  DeviceGuard guard(reinterpret_cast<gpm_handle_impl*>(h)->device);
   GPM_CUDA(cudaMemcpyAsync(alpha, Y, (size_t)N * R * sizeof(double), cudaMemcpyDeviceToDevice, st));
   gpm_handle_impl* hi = reinterpret_cast<gpm_handle_impl*>(h);
-  int rc = getenv("GPM_SOLVE_STEPS")
+  int rc = hi->opt.solve_steps
                ? solve_blocked(L, N, ldl, reinterpret_cast<const double*>(potrf_ws), alpha, R, 1, 0, 0, 0, st)
                : solve_chain(hi, L, N, ldl, reinterpret_cast<const double*>(potrf_ws), alpha, R, st);
   if (rc) return rc;

@@ -59,10 +59,19 @@ typedef struct gpm_grid {
 
 int         gpm_version(void);
 const char* gpm_last_error(void);                     /* thread-local text of the last failure */
+/* A handle carries mutable per-call state (a helper stream, an event pool, the flag arrays of the chained
+ * solves): it is SINGLE-STREAM and SINGLE-THREAD.  Calls that may overlap in time -- issued on different CUDA
+ * streams or from different host threads -- need one handle each (the Python binding keys its handles on
+ * (device, stream)).  Every entry point runs on the handle's device and restores the caller's current device. */
 int         gpm_create(gpm_handle_t* handle, int device);
 int         gpm_destroy(gpm_handle_t handle);
 int         gpm_sm_count(gpm_handle_t handle);
 long long   gpm_launch_count(void);                   /* kernels launched by this library so far (process-wide) */
+/* Debug / comparison switches of a handle (e.g. "no_lookahead", "no_separable", "var_steps", "no_path_fused";
+ * the full list is kOptions in csrc/api.cu).  Each is initialised ONCE, at gpm_create, from the environment
+ * variable GPM_<NAME>; no entry point reads the environment afterwards.  Returns -2 for an unknown name. */
+int         gpm_set_option(gpm_handle_t handle, const char* name, int value);
+int         gpm_get_option(gpm_handle_t handle, const char* name, int* value);
 
 /* Step 1.  K = k(X,X) + noise_var*I.  Replaces  cdist(X/l, X/l,'sqeuclidean') -> np.exp -> +sigma^2 I.
  * X: N x D row-major (ldx = D).  K: N x N, leading dimension ldk. */
@@ -94,8 +103,8 @@ int gpm_solve_lml(gpm_handle_t h, const double* L, int64_t N, int64_t ldl, const
 
 /* Step 4+5.  Posterior mean and variance at query points.
  *   mu[m, r] = sum_i k(xs_m, x_i) alpha[i, r]             (fused: K* is never stored)
- *   var[m]   = signal_var - || L^{-1} k(X, xs_m) ||^2      (blocked TRSM on FP64 tensor cores +
- *                                                           row-norm epilogue)
+ *   var[m]   = max(0, signal_var - || L^{-1} k(X, xs_m) ||^2)   (blocked TRSM on FP64 tensor cores + row-norm
+ *                                                           epilogue; clamped at 0 against cancellation)
  * Replaces  Ks.T @ alpha  and  solve_triangular(L, Ks) -> column sum of squares.
  * Query points: rows [m0, m1) of Xs (M_total x D) if Xs != NULL, else points [m0, m1) of `grid`
  * (so a caller shards the grid across GPUs by choosing [m0, m1)).  mu: (m1-m0) x R, var: (m1-m0);
@@ -111,10 +120,10 @@ int gpm_predict(gpm_handle_t h, const double* X, int64_t N, int32_t D, const dou
  * length).  Xb: B x N x D, Yb: B x N x R, theta: HOST pointer to (D+2) doubles shared by all
  * paths (theta_stride = 0) or to B x (D+2) per-path values (theta_stride = D+2; the host array must stay
  * valid until the copy enqueued on `stream` has run).  alpha: B x N x R (must not alias Yb), lml: B x R,
- * info: B device int32.  ws: gpm_fit_batched_workspace_bytes(B, N) bytes.
+ * info: B device int32.  ws: gpm_fit_batched_workspace_bytes(h, B, N) bytes.
  * Paths of N <= 112 samples (GPmap.py:189 resamples every trajectory to 33) are fitted one CTA per path entirely in
  * shared memory and B is limited only by 2^31; longer paths go through batched tile launches with B <= 65535. */
-size_t gpm_fit_batched_workspace_bytes(int64_t B, int64_t N);
+size_t gpm_fit_batched_workspace_bytes(gpm_handle_t h, int64_t B, int64_t N);
 int gpm_fit_batched(gpm_handle_t h, const double* Xb, const double* Yb, int64_t B, int64_t N,
                     int32_t D, int32_t R, const double* theta, int64_t theta_stride,
                     double* alpha, double* lml, int32_t* info, void* ws, gpm_stream_t stream);
@@ -128,13 +137,31 @@ int gpm_lml_grad(gpm_handle_t h, const double* X, int64_t N, int32_t D, const do
                  const double* L, int64_t ldl, const void* potrf_ws, const double* alpha, int32_t R,
                  double* grad, void* ws, size_t ws_bytes, gpm_stream_t stream);
 
-/* "Next" row of SURVEY.md section 8f: the reference's actual hot loop, trajectories.calc_distance
- * inside kmeansclustering (GPmap.py:72-80,114-121): dist[p, c] = sum_i ||path_p[i] - centroid_c[i]||_2,
- * assign[p] = first c with the smallest distance (strict '<' as GPmap.py:76).
- * px, py: P x n; cx, cy: k x n row-major device arrays. */
-int gpm_kmeans_assign(gpm_handle_t h, const double* px, const double* py, int64_t P, int32_t n,
+/* "Next" row of SURVEY.md section 8f: the reference's actual hot loop, trajectories.kmeansclustering
+ * (GPmap.py:36-93), as a kernel pair that keeps the Lloyd iteration on the device.
+ *
+ * gpm_kmeans_assign -- one assignment step (GPmap.py:72-80,114-121): dist[p, c] = sum_i ||path_p[i] - centroid_c[i]||_2
+ * summed sequentially in sample order, assign[p] = first c with the smallest distance (strict '<' as GPmap.py:76).
+ * pxT, pyT: n x P (SAMPLE-major, so that a warp's loads are contiguous); cx, cy: k x n; dist (P x k) may be NULL.
+ *
+ * gpm_kmeans_lloyd -- `iters` (even) full iterations enqueued back to back: assignment, centroid update
+ * (calc_mean_traj, GPmap.py:95-112: members summed in path order, then divided by the count -- bit-exact; an empty
+ * cluster keeps its centroid) and the convergence test shift = sum_c calc_distance(new_c, old_c) < threshold
+ * (GPmap.py:87-90).  Once converged, the remaining kernels of the call are no-ops.  px, py, pt: P x n path-major
+ * copies of xs, ys, timestamp; pxT, pyT: n x P.  centroids: 3 x k x n (xs, ys, timestamp planes), in/out.
+ * first != 0 resets the device-side state in ws (gpm_kmeans_workspace_bytes).  gpm_kmeans_state reads that state
+ * (synchronises the stream): when *iters is odd the final centroids are the first 3*k*n doubles of ws, otherwise
+ * they are in `centroids`. */
+int gpm_kmeans_assign(gpm_handle_t h, const double* pxT, const double* pyT, int64_t P, int32_t n,
                       const double* cx, const double* cy, int32_t k, double* dist, int32_t* assign,
                       gpm_stream_t stream);
+size_t gpm_kmeans_workspace_bytes(int64_t P, int32_t n, int32_t k);
+int gpm_kmeans_lloyd(gpm_handle_t h, const double* px, const double* py, const double* pt,
+                     const double* pxT, const double* pyT, int64_t P, int32_t n, int32_t k,
+                     double* centroids, int32_t* assign, double threshold, int32_t iters, int32_t first,
+                     void* ws, gpm_stream_t stream);
+int gpm_kmeans_state(gpm_handle_t h, const void* ws, int32_t n, int32_t k, int32_t* iters,
+                     int32_t* converged, double* shift, gpm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -226,3 +226,38 @@ def travel_sum(xs, ys):
     n = len(xs)
     w = 2.0 * np.arange(n) - (n - 1)
     return float(np.sum(w * (np.abs(xs) + np.abs(ys))))
+
+
+def lloyd(xs, ys, ts, init_idx, threshold=5.0, max_iter=1000):
+    """The Lloyd loop of trajectories.kmeansclustering (GPmap.py:65-93) from fixed initial centroids.
+
+    xs, ys, ts: (P, n).  init_idx: indices of the k paths copied as initial centroids (GPmap.py:58-60).
+    Every path joins the first centroid with the smallest calc_distance (strict '<', GPmap.py:72-80), centroids
+    become calc_mean_traj of their members in path order (GPmap.py:83-84), and the loop stops when the summed
+    centroid shift is below ``threshold`` (GPmap.py:87-90).  Returns (assign (P,), centroids (3, k, n), iterations).
+    An empty cluster keeps its centroid (the reference divides by zero there, GPmap.py:111).
+    """
+    P, n = xs.shape
+    k = len(init_idx)
+    cx = xs[list(init_idx)].copy(); cy = ys[list(init_idx)].copy(); ct = ts[list(init_idx)].copy()
+    assign = np.zeros(P, dtype=np.int64)
+    for it in range(1, max_iter + 1):
+        for p in range(P):
+            best, best_c = None, 0
+            for c in range(k):
+                d = calc_distance(cx[c], cy[c], xs[p], ys[p])
+                if best is None or d < best:
+                    best, best_c = d, c
+            assign[p] = best_c
+        nx, ny, nt = cx.copy(), cy.copy(), ct.copy()
+        for c in range(k):
+            mem = np.nonzero(assign == c)[0]
+            if len(mem):
+                nx[c], ny[c], nt[c] = calc_mean_traj(xs[mem], ys[mem], ts[mem])
+        tot = 0
+        for c in range(k):
+            tot += calc_distance(nx[c], ny[c], cx[c], cy[c])
+        cx, cy, ct = nx, ny, nt
+        if tot < threshold:
+            return assign, np.stack([cx, cy, ct]), it
+    return assign, np.stack([cx, cy, ct]), max_iter

@@ -35,7 +35,8 @@ def test_workspace_queries_need_no_gpu():
     lib = _native.load()
     assert lib.gpm_potrf_workspace_bytes(4096) == 32 * 128 * 128 * 8
     assert lib.gpm_potrf_workspace_bytes(200) == 2 * 128 * 128 * 8
-    assert lib.gpm_fit_batched_workspace_bytes(3, 512) == 3 * (512 * 512 + 512 * 128 + 8 + 512 * 8) * 8
+    assert lib.gpm_fit_batched_workspace_bytes(None, 3, 512) == 0      # depends on the handle's options: needs a handle
+    assert lib.gpm_kmeans_workspace_bytes(100, 33, 3) == (3 * 3 * 33 + 3 + 2) * 8
     assert lib.gpm_potrf_workspace_bytes(0) == 0
 
 

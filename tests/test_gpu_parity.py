@@ -91,11 +91,8 @@ def test_potrf_lookahead_equals_plain():
     X, _, th = wl.single_path(900, seed=5, D=2)
     Ko = gp_ref.cov(X, th)
     L1, _, _ = gpu_potrf(Ko)
-    os.environ["GPM_NO_LOOKAHEAD"] = "1"
-    try:
+    with _native.option("no_lookahead", 1):
         L2, _, _ = gpu_potrf(Ko)
-    finally:
-        del os.environ["GPM_NO_LOOKAHEAD"]
     assert np.array_equal(L1, L2)                # same kernels, same order of arithmetic
 
 
@@ -192,17 +189,18 @@ def test_batched_golden_and_oracle(golden):
     one = GPmap.fit_gp(Xb[2], Yb[2], theta=th)
     assert nrm(alpha[2].cpu().numpy(), one.alpha.cpu().numpy()) < 1e-12
 
-def test_batched_fused_forward_matches_separate_solve(monkeypatch):
-    """The forward substitution fused into the factorisation (default for N <= 2048) against the
-    solve kernel running both passes (GPM_NO_FUSED_FWD), for odd / full right-hand-side counts."""
+def test_batched_fused_forward_matches_separate_solve():
+    """Tiled batched pipeline (option no_path_fused): the forward substitution fused into the factorisation
+    (default for N <= 2048) against the solve kernel running both passes (option no_fused_fwd), for odd / full
+    right-hand-side counts."""
     for (B, N, D, R) in ((5, 300, 2, 3), (3, 130, 3, 1), (2, 512, 2, 8)):
         Xb, Yb, th = wl.batched_paths(B, N, seed=4, D=D, R=2)
         rng = np.random.default_rng(R)
         Yb = np.ascontiguousarray(np.concatenate([Yb, Yb.std() * rng.standard_normal((B, N, 6))], axis=2)[:, :, :R])
-        monkeypatch.delenv("GPM_NO_FUSED_FWD", raising=False)
-        a1, l1 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
-        monkeypatch.setenv("GPM_NO_FUSED_FWD", "1")
-        a0, l0 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+        with _native.option("no_path_fused", 1):
+            a1, l1 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+            with _native.option("no_fused_fwd", 1):
+                a0, l0 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
         a_o, l_o = gp_ref.fit_batched(Xb, Yb, th)
         assert nrm(a1.cpu().numpy(), a0.cpu().numpy()) < 1e-12
         assert nrm(a1.cpu().numpy(), a_o) < MEAN_TOL
@@ -233,6 +231,40 @@ def test_kmeans_assign_matches_reference(ref_golden):
     assert np.abs(dist - g["d2c"]).max() <= 1e-15 * g["d2c"].max()
     clusters = T.kmeansclustering(3, seed=1)
     assert sorted(k for v in clusters.values() for k in v) == sorted(T.pathdict)
+
+
+def test_kmeans_device_lloyd_matches_the_reference_run():
+    """The device-resident Lloyd loop (assign + segmented mean + convergence kernels, paths uploaded once) against a
+    full run of the reference's own kmeansclustering from the same initial centroids
+    (tests/golden/reference_kmeans_golden.npz): same iteration count and assignment, bit-identical centroids."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_kmeans_golden.npz"))
+    for tag in ("a", "b"):
+        keys = g[f"{tag}_keys"].tolist()
+        T = GPmap.trajectories()
+        for i, k in enumerate(keys):
+            t = GPmap.trajectory(); t.xs, t.ys, t.timestamp = g[f"{tag}_xs"][i], g[f"{tag}_ys"][i], g[f"{tag}_ts"][i]
+            T.add_trajectory(k, t)
+        init = g[f"{tag}_init"].tolist()
+        clusters = T.kmeansclustering(len(init), init=init)
+        assert T.kmeans_iterations == int(g[f"{tag}_iters"])
+        names = list(clusters)
+        got = np.array([next(c for c, nm in enumerate(names) if key in clusters[nm]) for key in keys])
+        assert np.array_equal(got, g[f"{tag}_assign"])
+        cents = np.stack([np.stack([T.centroids[nm].xs for nm in names]), np.stack([T.centroids[nm].ys for nm in names]),
+                          np.stack([T.centroids[nm].timestamp for nm in names])])
+        assert np.array_equal(cents, g[f"{tag}_cents"])
+        for nm in names:                                       # members listed in path order, as the reference appends them
+            assert clusters[nm] == [k for k in keys if k in clusters[nm]]
+    # an empty cluster keeps its centroid instead of dividing by zero (GPmap.py:111): two identical initial centroids
+    T = GPmap.trajectories()
+    for i, k in enumerate(g["a_keys"].tolist()):
+        t = GPmap.trajectory(); t.xs, t.ys, t.timestamp = g["a_xs"][i], g["a_ys"][i], g["a_ts"][i]
+        T.add_trajectory(k, t)
+    dup = GPmap.trajectory(); dup.xs, dup.ys, dup.timestamp = g["a_xs"][0].copy(), g["a_ys"][0].copy(), g["a_ts"][0].copy()
+    T.add_trajectory("dup", dup)
+    clusters = T.kmeansclustering(3, init=[g["a_keys"][0], "dup", g["a_keys"][7]])
+    assert sorted(k for v in clusters.values() for k in v) == sorted(T.pathdict)
+    assert T.kmeans_iterations >= 1 and all(np.isfinite(c.xs).all() for c in T.centroids.values())
 
 
 def test_config2_size_against_oracle_and_properties():
@@ -337,17 +369,11 @@ def test_variance_chunked_workspace_and_per_step_path_agree():
 
     mu_c, var_c = run(384)                      # 14 chunks of 384 rows
     assert torch.equal(mu_c, mu_full) and torch.equal(var_c, var_full)
-    os.environ["GPM_NO_FUSED_MEAN"] = "1"       # separate mean kernel: same values up to summation order
-    try:
+    with _native.option("no_fused_mean", 1):    # separate mean kernel: same values up to summation order
         mu_n, var_n = run(384)
-    finally:
-        del os.environ["GPM_NO_FUSED_MEAN"]
     assert torch.equal(var_n, var_full) and float((mu_n - mu_full).abs().max()) <= 1e-12 * float(mu_full.abs().max())
-    os.environ["GPM_VAR_STEPS"] = "1"
-    try:
+    with _native.option("var_steps", 1):
         mu_s, var_s = run(1024)
-    finally:
-        del os.environ["GPM_VAR_STEPS"]
     assert torch.equal(var_s, var_full)
     mo = gp_ref.fit(X, Y, th)
     _, var_o = gp_ref.predict(mo, Xs.cpu().numpy())
@@ -541,9 +567,9 @@ def test_config5_size_grid_slice_against_oracle():
     assert torch.equal(mu2[300:], mu) and torch.allclose(var2[300:], var, rtol=0, atol=1e-13)
 
 
-def test_separable_grid_kernels_match_the_pointwise_ones(monkeypatch):
+def test_separable_grid_kernels_match_the_pointwise_ones():
     """Grid queries use the separable form of the RBF kernel (PA + PB exponentials per patch and training point);
-    the pointwise kernels (GPM_NO_SEPARABLE, also what predict(Xs) runs) must agree to rounding, for ragged grids,
+    the pointwise kernels (option no_separable, also what predict(Xs) runs) must agree to rounding, for ragged grids,
     D = 3 with a query time, R up to 8, and flat sub-ranges that start and end inside grid rows."""
     for (N, D, R, G, t) in ((300, 2, 2, (37, 23), None), (257, 3, 1, (5, 70), 31.0), (140, 2, 8, (130, 9), None)):
         X, Y, th = wl.single_path(N, seed=6, D=D, R=2)
@@ -552,12 +578,10 @@ def test_separable_grid_kernels_match_the_pointwise_ones(monkeypatch):
         m = GPmap.fit_gp(X, Y, theta=th)
         M = G[0] * G[1]
         for pts in (None, (G[0] + 3, M - 5), (7, 9)):
-            monkeypatch.delenv("GPM_NO_SEPARABLE", raising=False)
             mu1, var1 = m.predict_grid(wl.BOX, G, t=t, points=pts)
             mo1 = m.predict_grid(wl.BOX, G, t=t, points=pts, return_var=False)
-            monkeypatch.setenv("GPM_NO_SEPARABLE", "1")
-            mu0, var0 = m.predict_grid(wl.BOX, G, t=t, points=pts)
-            monkeypatch.delenv("GPM_NO_SEPARABLE", raising=False)
+            with _native.option("no_separable", 1):
+                mu0, var0 = m.predict_grid(wl.BOX, G, t=t, points=pts)
             assert torch.equal(mo1, mu1)                                   # mean-only and mean+variance calls agree bitwise
             assert nrm(mu1.cpu().numpy(), mu0.cpu().numpy()) < 1e-12
             assert nrm(var1.cpu().numpy(), var0.cpu().numpy()) < 1e-11
@@ -572,20 +596,18 @@ def test_separable_grid_kernels_match_the_pointwise_ones(monkeypatch):
         assert nrm(mu1.reshape(-1, R).cpu().numpy(), mu2.cpu().numpy()) < 1e-12
 
 
-def test_short_paths_one_cta_per_path_kernel(monkeypatch):
+def test_short_paths_one_cta_per_path_kernel():
     """N <= 112 (the reference resamples trajectories to 33 points, GPmap.py:189): the whole fit runs in one CTA per
-    path.  Against the oracle, against the tiled pipeline (GPM_NO_SMALL_FUSED), with per-path hyper-parameters, and
+    path.  Against the oracle, against the tiled pipeline (option no_small_fused), with per-path hyper-parameters, and
     the LAPACK-style info of a path that is not positive definite."""
     for (B, N, D, R) in ((7, 33, 2, 2), (3, 1, 2, 1), (4, 2, 3, 2), (5, 64, 3, 3), (3, 100, 2, 8), (6, 112, 3, 2)):
         Xb, Yb, th = wl.batched_paths(B, max(N, 4), seed=11, D=D, R=2)
         Xb, Yb = np.ascontiguousarray(Xb[:, :N]), Yb[:, :N]
         rng = np.random.default_rng(N)
         Yb = np.ascontiguousarray(np.concatenate([Yb, rng.standard_normal((B, N, 6))], axis=2)[:, :, :R])
-        monkeypatch.delenv("GPM_NO_SMALL_FUSED", raising=False)
         a1, l1 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
-        monkeypatch.setenv("GPM_NO_SMALL_FUSED", "1")
-        a0, l0 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
-        monkeypatch.delenv("GPM_NO_SMALL_FUSED", raising=False)
+        with _native.option("no_small_fused", 1), _native.option("no_path_fused", 1):
+            a0, l0 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
         a_o, l_o = gp_ref.fit_batched(Xb, Yb, th)
         assert nrm(a1.cpu().numpy(), a_o) < MEAN_TOL
         assert np.abs(l1.cpu().numpy() - l_o).max() < LML_TOL * max(np.abs(l_o).max(), 1.0)
@@ -610,18 +632,16 @@ def test_short_paths_one_cta_per_path_kernel(monkeypatch):
     assert nrm(am[-3:].cpu().numpy(), a_o) < MEAN_TOL and bool(torch.isfinite(lm).all())
 
 
-def test_latency_tile_kernel_is_bitwise_the_tile_kernel(monkeypatch):
+def test_latency_tile_kernel_is_bitwise_the_tile_kernel():
     """Launches of at most 37 tiles (every tile launch of a fit with N <= 4096, the tail of a large one) split each
     128x128 tile into four 64x64 quarters on four SMs (gemm_small.cu).  Same DMMA sequence per element: the factor must
     not change by a single bit, for full and ragged last blocks."""
     for N in (129, 900, 2048, 4096 + 77):
         X, _, th = wl.single_path(N, seed=7, D=2)
         Ko = gp_ref.cov(X, th)
-        monkeypatch.delenv("GPM_NO_SMALL_TILES", raising=False)
         L1, ws1, info1 = gpu_potrf(Ko)
-        monkeypatch.setenv("GPM_NO_SMALL_TILES", "1")
-        L0, ws0, info0 = gpu_potrf(Ko)
-        monkeypatch.delenv("GPM_NO_SMALL_TILES", raising=False)
+        with _native.option("no_small_tiles", 1):
+            L0, ws0, info0 = gpu_potrf(Ko)
         assert info1 == 0 and info0 == 0
         assert np.array_equal(L1, L0)
         assert torch.equal(ws1, ws0)

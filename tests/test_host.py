@@ -71,3 +71,17 @@ def test_packed_and_theta():
     assert Xb.shape == (len(keys), 33, 3) and Xb.dtype == np.float64
     assert GPmap.make_theta(8000.0, 1.0, 0.01, 3).tolist() == [8000.0, 8000.0, 8000.0, 1.0, 0.01]
     assert GPmap.make_theta([1.0, 2.0], 3.0, 4.0, 2).tolist() == [1.0, 2.0, 3.0, 4.0]
+
+
+def test_lloyd_restatement_matches_the_reference_run():
+    """oracle.gp_ref.lloyd against a full run of the reference's own kmeansclustering (fixed initial centroids,
+    tests/golden/make_reference_kmeans_golden.py): same iteration count, assignment and bit-identical centroids."""
+    from oracle import gp_ref
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_kmeans_golden.npz"))
+    for tag in ("a", "b"):
+        keys = g[f"{tag}_keys"].tolist()
+        init = [keys.index(k) for k in g[f"{tag}_init"].tolist()]
+        assign, cents, iters = gp_ref.lloyd(g[f"{tag}_xs"], g[f"{tag}_ys"], g[f"{tag}_ts"], init)
+        assert iters == int(g[f"{tag}_iters"])
+        assert np.array_equal(assign, g[f"{tag}_assign"])
+        assert np.array_equal(cents, g[f"{tag}_cents"])
