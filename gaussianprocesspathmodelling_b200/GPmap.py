@@ -323,11 +323,14 @@ def fit_gp(X, Y, lengthscale=None, signal_var=1.0, noise_var=1e-2, theta=None, c
     return model
 
 
-def fit_gp_batched(Xb, Yb, lengthscale=None, signal_var=1.0, noise_var=1e-2, theta=None, check=True, workspace=None):
+def fit_gp_batched(Xb, Yb, lengthscale=None, signal_var=1.0, noise_var=1e-2, theta=None, check=True, workspace=None,
+                   out=None):
     """B independent equal-length paths: Xb (B, N, D), Yb (B, N, R) -> alpha (B, N, R), lml (B, R) (CUDA).
 
     Paths of up to 112 samples (the reference resamples to 33, GPmap.py:189) are fitted one CTA per path entirely in
-    shared memory; longer ones go through the tiled tensor-core pipeline (B <= 65535 there)."""
+    shared memory; up to 1024 samples one CTA per path with tensor-core tiles (two paths in flight per SM); longer
+    ones go through the tiled batched pipeline (B <= 65535 there).  ``workspace``: caller-owned scratch;
+    ``out=(alpha, lml)``: caller-owned result buffers."""
     torch = _torch()
     lib = _native.load()
     Xb = _dev(Xb)
@@ -343,8 +346,13 @@ def fit_gp_batched(Xb, Yb, lengthscale=None, signal_var=1.0, noise_var=1e-2, the
         raise ValueError(f"theta must have shape ({D + 2},) or ({B}, {D + 2})")
     stride = D + 2 if theta.ndim == 2 else 0
     h = _native.handle(Xb.device.index or 0)
-    alpha = torch.empty((B, N, R), dtype=torch.float64, device=Xb.device)
-    lml = torch.empty((B, R), dtype=torch.float64, device=Xb.device)
+    if out is not None:                      # caller-owned results (e.g. this rank's slices of an all-gather buffer)
+        alpha, lml = out
+        if alpha.shape != (B, N, R) or lml.shape != (B, R) or not alpha.is_contiguous() or not lml.is_contiguous():
+            raise ValueError("out= must be contiguous (B, N, R) and (B, R) float64 CUDA tensors")
+    else:
+        alpha = torch.empty((B, N, R), dtype=torch.float64, device=Xb.device)
+        lml = torch.empty((B, R), dtype=torch.float64, device=Xb.device)
     info = torch.zeros(B, dtype=torch.int32, device=Xb.device)
     ws = _workspace(int(lib.gpm_fit_batched_workspace_bytes(h, B, N)), Xb.device, "fit_batched", workspace)
     th_arr = _native.theta_array(theta.ravel())

@@ -261,3 +261,53 @@ def lloyd(xs, ys, ts, init_idx, threshold=5.0, max_iter=1000):
         if tot < threshold:
             return assign, np.stack([cx, cy, ct]), it
     return assign, np.stack([cx, cy, ct]), max_iter
+
+
+# ----------------------------------------------------------------------------------------------
+# Timed variants for bench.py's CPU baseline: the same calls as fit() / predict(), with wall-clock per step
+# (cov / cholesky / solve+LML / mean / variance reported separately).
+# ----------------------------------------------------------------------------------------------
+
+def fit_phases(X, Y, theta):
+    """fit() with per-step wall times: returns (model, {"cov_s", "cholesky_s", "solve_lml_s"})."""
+    import time
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.ndim == 1:
+        Y = Y[:, None]
+    N = X.shape[0]
+    t0 = time.perf_counter()
+    K = cov(X, theta)
+    t1 = time.perf_counter()
+    L = cholesky(K, lower=True)
+    t2 = time.perf_counter()
+    z = solve_triangular(L, Y, lower=True)
+    alpha = solve_triangular(L, z, lower=True, trans="T")
+    lml = -0.5 * np.einsum("nr,nr->r", Y, alpha) - np.log(np.diag(L)).sum() - 0.5 * N * LOG_2PI
+    t3 = time.perf_counter()
+    model = {"X": X, "theta": np.asarray(theta, dtype=np.float64), "L": L, "alpha": alpha, "lml": lml}
+    return model, {"cov_s": t1 - t0, "cholesky_s": t2 - t1, "solve_lml_s": t3 - t2}
+
+
+def predict_phases(model, Xs, tile=8192):
+    """predict() with per-step wall times: returns (mu, var, {"cross_cov_s", "mean_s", "var_s"})."""
+    import time
+    Xs = np.asarray(Xs, dtype=np.float64)
+    X, theta, L, alpha = model["X"], model["theta"], model["L"], model["alpha"]
+    _, sf2, _ = split_theta(theta, X.shape[1])
+    M = Xs.shape[0]
+    mu = np.empty((M, alpha.shape[1]))
+    var = np.empty(M)
+    tm = {"cross_cov_s": 0.0, "mean_s": 0.0, "var_s": 0.0}
+    for m0 in range(0, M, tile):
+        m1 = min(M, m0 + tile)
+        t0 = time.perf_counter()
+        Ks = cross_cov(X, Xs[m0:m1], theta)
+        t1 = time.perf_counter()
+        mu[m0:m1] = Ks.T @ alpha
+        t2 = time.perf_counter()
+        V = solve_triangular(L, Ks, lower=True)
+        var[m0:m1] = sf2 - np.einsum("nm,nm->m", V, V)
+        t3 = time.perf_counter()
+        tm["cross_cov_s"] += t1 - t0; tm["mean_s"] += t2 - t1; tm["var_s"] += t3 - t2
+    return mu, var, tm

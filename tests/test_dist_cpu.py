@@ -43,7 +43,15 @@ def _worker(rank, world, port, n, q):
         full2 = torch.arange(8, dtype=torch.float64)
         lo, hi = gdist.shard_range(8, rank, world)
         got2 = gdist.all_gather_rows(full2[lo:hi].clone(), gdist.shard_counts(8, world))
-        q.put((rank, bool(ok and torch.equal(got2, full2))))
+        # in place: every rank fills only its slice of the full buffer, the gather completes it (even and uneven)
+        ok3 = True
+        for m in (8, 7):
+            want = torch.arange(m * 2, dtype=torch.float64).view(m, 2)
+            buf = torch.full((m, 2), -1.0, dtype=torch.float64)
+            lo, hi = gdist.shard_range(m, rank, world)
+            buf[lo:hi] = want[lo:hi]
+            ok3 = ok3 and torch.equal(gdist.all_gather_inplace(buf, gdist.shard_counts(m, world)), want)
+        q.put((rank, bool(ok and ok3 and torch.equal(got2, full2))))
     finally:
         dist.destroy_process_group()
 
