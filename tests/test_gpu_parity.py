@@ -648,3 +648,47 @@ def test_latency_tile_kernel_is_bitwise_the_tile_kernel():
         if N <= 2048:
             Lo = scipy.linalg.cholesky(Ko, lower=True)
             assert nrm(L1, Lo) < 1e-9
+
+
+def test_two_streams_concurrent_fits_equal_the_serial_result_bitwise():
+    """A library handle is single-stream state (helper stream, events, the flags of the chained solves); the Python
+    binding keys its handles -- and its cached workspaces -- on (device, stream), so two host threads driving two
+    CUDA streams at once cannot race.  Each must reproduce the serial result bit for bit."""
+    import threading
+    X, Y, th = wl.single_path(1500, seed=31, D=2, R=2)
+    X2, Y2, th2 = wl.single_path(1100, seed=32, D=2, R=1)
+    Xd, Yd, X2d, Y2d = dev(X), dev(Y), dev(X2), dev(Y2)
+    shape = (96, 80)
+
+    def work(Xa, Ya, tha):
+        m = GPmap.fit_gp(Xa, Ya, theta=tha, check=False)
+        mu, var = m.predict_grid(wl.BOX, shape)
+        return m.alpha.clone(), m.lml_dev.clone(), mu.clone(), var.clone()
+
+    want = [work(Xd, Yd, th), work(X2d, Y2d, th2)]
+    torch.cuda.synchronize()
+    n0 = len(_native._handles)
+    got = [None, None]
+    errs = []
+
+    def runner(i, Xa, Ya, tha):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(4):
+                    out = work(Xa, Ya, tha)
+                s.synchronize()
+            got[i] = out
+        except Exception as e:                                   # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=runner, args=(0, Xd, Yd, th)), threading.Thread(target=runner, args=(1, X2d, Y2d, th2))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    assert len(_native._handles) >= n0 + 2                     # one handle per stream
+    for w, g in zip(want, got):
+        for a, b in zip(w, g):
+            assert torch.equal(a, b)
