@@ -132,8 +132,9 @@ static int create_impl(gpm_handle_impl* h, int device) {
     h->n_ev = i + 1;
   }
   h->n_flags = 8192;                  // up to N = 2^20
+  // (no memset here: every solve clears the flags on its own stream, and a synchronous memset would invalidate a
+  //  CUDA-graph capture in progress -- the Python binding creates the handle of a new stream on first use)
   GPM_CUDA(cudaMalloc(&h->flags, 2 * h->n_flags * sizeof(int)));
-  GPM_CUDA(cudaMemset(h->flags, 0, 2 * h->n_flags * sizeof(int)));
   return 0;
 }
 

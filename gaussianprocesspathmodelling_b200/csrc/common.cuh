@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include "../../include/gpmap_b200.h"
+#include "exp_neg.cuh"
 
 #define NB GPM_NB            // factorisation block / GEMM tile edge (128)
 #define SLAB_K 16            // contraction depth of one TMA slab: 16 doubles = 128 B = one swizzle row
@@ -188,7 +189,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // RBF kernel value from pre-scaled coordinates (x/l): sf2 * exp(-0.5 * |a-b|^2).  The squared
 // distance is summed unfused and in dimension order, as scipy's cdist 'sqeuclidean' does, so K
-// differs from the oracle's only by the exp() implementation (both < 1 ulp).
+// differs from the oracle's only by the exp() implementation (gpm_exp_neg: < 0.51 ulp, 12 FP64-pipe instructions).
 template <int D>
 __device__ __forceinline__ double rbf(const double* a, const double* b, double sf2) {
   double dx = a[0] - b[0], dy = a[1] - b[1];
@@ -197,7 +198,7 @@ __device__ __forceinline__ double rbf(const double* a, const double* b, double s
     double dz = a[2] - b[2];
     d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
   }
-  return sf2 * exp(-0.5 * d2);
+  return sf2 * gpm_exp_neg_half(d2);
 }
 
 // coordinates of grid point m (matches numpy.linspace: start + i*step, last point = stop exactly)

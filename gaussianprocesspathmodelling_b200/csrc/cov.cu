@@ -115,15 +115,15 @@ cross_cov_t_kernel(const double* __restrict__ X, long long N, Theta th, const do
 }
 
 // Fused cross-covariance + posterior mean (used when the variance is wanted too, so K*^T has to be
-// materialised anyway): a CTA owns 8 query rows and walks all training columns, 256 at a time; every
+// materialised anyway): a CTA owns QR query rows (8 for R <= 2, 4 for more right-hand sides: the QR x R partial
+// sums live in registers) and walks all training columns, 256 at a time; every
 // k(xs_m, x_i) is evaluated once, stored to KsT (coalesced 2 KB row segments) and accumulated into the
 // mean; the 8 x R partial sums are reduced across the CTA at the end (fixed order: deterministic).
-template <int D, int RR>
+template <int D, int RR, int QR>
 __global__ void __launch_bounds__(256)
 cross_cov_mean_kernel(const double* __restrict__ X, long long N, Theta th, const double* __restrict__ alpha, int R,
                       const double* __restrict__ Xs, gpm_grid_t grid, int use_grid, long long m0, long long M,
                       double* __restrict__ KsT, long long ldks, long long ncols_pad, double* __restrict__ mu) {
-  constexpr int QR = 8;
   __shared__ double q[QR][3];
   __shared__ double red[8][QR * RR];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -290,7 +290,7 @@ cross_cov_grid_kernel(const double* __restrict__ X, long long N, Theta th, gpm_g
       py = X[i * D + 1] / th.l[1];
       if (D == 3) { const double dt = qt - X[i * D + 2] / th.l[2]; dt2 = __dmul_rn(dt, dt); }
 #pragma unroll
-      for (int r = 0; r < PA; r++) { const double dx = qx[r] - px; ex[r] = exp(-0.5 * __dmul_rn(dx, dx)); }
+      for (int r = 0; r < PA; r++) { const double dx = qx[r] - px; ex[r] = gpm_exp_neg_half(__dmul_rn(dx, dx)); }
     } else {
 #pragma unroll
       for (int r = 0; r < PA; r++) ex[r] = 0.0;
@@ -302,7 +302,7 @@ cross_cov_grid_kernel(const double* __restrict__ X, long long N, Theta th, gpm_g
       if (rm == 0) continue;
       const double dy = sqy[rb] - py;
       const double d2 = D == 3 ? __dadd_rn(__dmul_rn(dy, dy), dt2) : __dmul_rn(dy, dy);
-      const double ey = in ? th.sf2 * exp(-0.5 * d2) : 0.0;
+      const double ey = in ? th.sf2 * gpm_exp_neg_half(d2) : 0.0;
 #pragma unroll
       for (int ra = 0; ra < PA; ra++)
         if (rm >> ra & 1) prow[ra * ldks] = ex[ra] * ey;
@@ -344,12 +344,12 @@ predict_mean_grid_kernel(const double* __restrict__ X, long long N, Theta th, co
       if (c < n) {
         if (which == 0) {
           const double dx = sq[0][r] - sx[c][0];
-          exs[c][r] = exp(-0.5 * __dmul_rn(dx, dx));
+          exs[c][r] = gpm_exp_neg_half(__dmul_rn(dx, dx));
         } else {
           const double dy = sq[1][r] - sx[c][1];
           double d2 = __dmul_rn(dy, dy);
           if (D == 3) { const double dt = qt - sx[c][2]; d2 = __dadd_rn(d2, __dmul_rn(dt, dt)); }
-          eys[c][r] = th.sf2 * exp(-0.5 * d2);
+          eys[c][r] = th.sf2 * gpm_exp_neg_half(d2);
         }
       }
     }
@@ -413,9 +413,11 @@ template <int D>
 static int launch_ccm_d(const double* X, long long N, const Theta& th, const double* alpha, int R, const double* Xs,
                         const gpm_grid_t& g, int use_grid, long long m0, long long M, double* KsT, long long ldks,
                         long long ncols_pad, double* mu, cudaStream_t stream) {
-  const unsigned blocks = (unsigned)((M + 7) / 8);
-  if (R <= 1) cross_cov_mean_kernel<D, 1><<<blocks, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad, mu);
-  else if (R <= 2) cross_cov_mean_kernel<D, 2><<<blocks, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad, mu);
+  const unsigned b8 = (unsigned)((M + 7) / 8), b4 = (unsigned)((M + 3) / 4);
+  if (R <= 1) cross_cov_mean_kernel<D, 1, 8><<<b8, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad, mu);
+  else if (R <= 2) cross_cov_mean_kernel<D, 2, 8><<<b8, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad, mu);
+  else if (R <= 4) cross_cov_mean_kernel<D, 4, 4><<<b4, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad, mu);
+  else if (R <= 8) cross_cov_mean_kernel<D, 8, 4><<<b4, 256, 0, stream>>>(X, N, th, alpha, R, Xs, g, use_grid, m0, M, KsT, ldks, ncols_pad, mu);
   else return -1;
   GPM_LAUNCH_CHECK();
   return 0;

@@ -165,10 +165,10 @@ gemm_nt_strip_kernel(const GemmArgs p) {
   constexpr int STAGE = (SR + NB) * PITCH;
   auto stage = [&](int chunk, int buf) {
 #pragma unroll
-    for (int u = 0; u < 5; u++) {
-      const int piece = tid + SMALL_THREADS * u;          // 0..1279: 256 pieces of A (32 rows), 1024 of B (128 rows)
-      const bool isb = piece >= SR * 8;
-      const int pp = isb ? piece - SR * 8 : piece;
+    for (int u = 0; u < 10; u++) {
+      const int piece = tid + SMALL_THREADS * u;          // 0..2559: 512 16-byte pieces of A (32 rows), 2048 of B (128 rows)
+      const bool isb = piece >= SR * 16;
+      const int pp = isb ? piece - SR * 16 : piece;
       const int r = pp >> 4, c16 = pp & 15;
       const long long grow = isb ? min(b_row + r, b_rows_end - 1) : min(a_row + r, a_rows_end - 1);
       const double* src = isb ? p.small_B + grow * p.small_ldb + p.b_col0 + chunk * KC + c16 * 2

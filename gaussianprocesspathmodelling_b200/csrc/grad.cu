@@ -85,7 +85,7 @@ lml_grad_partial_kernel(const double* __restrict__ X, long long N, Theta th, con
       double d2 = 0.0;
 #pragma unroll
       for (int d = 0; d < D; d++) { const double t = xi[r][d] - xj[c][d]; dd[d] = t * t; d2 += dd[d]; }
-      const double kf = w * th.sf2 * exp(-0.5 * d2);
+      const double kf = w * th.sf2 * gpm_exp_neg_half(d2);
       double aa[GMAXR];
 #pragma unroll
       for (int k = 0; k < GMAXR; k++) aa[k] = ai[r][k] * aj[c][k];

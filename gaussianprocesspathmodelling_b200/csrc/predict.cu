@@ -80,9 +80,9 @@ extern "C" int gpm_predict(gpm_handle_t handle, const double* X, int64_t N, int3
     GPM_ARG(alpha != nullptr, 9);
     GPM_ARG(R >= 1 && R <= 8, 10);
     GPM_ARG(mu != nullptr, 15);
-    // with the variance requested and R <= 2 the mean is fused into the cross-covariance pass below
+    // with the variance requested the mean is fused into the cross-covariance pass below
     // (grid queries: the separable mean kernel + the separable cross-covariance are cheaper than the fused pass)
-    fuse_mean = (flags & GPM_PREDICT_VAR) && R <= 2 && !h->opt.no_fused_mean &&
+    fuse_mean = (flags & GPM_PREDICT_VAR) && R <= 8 && !h->opt.no_fused_mean &&
                 !(Xs == nullptr && grid_separable_enabled(h, grid, m0, M));
     if (!fuse_mean && (rc = launch_predict_mean(h, X, N, D, th, alpha, R, Xs, grid, m0, M, mu, st))) return rc;
   }
