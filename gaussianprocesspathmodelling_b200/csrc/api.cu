@@ -160,7 +160,13 @@ int gpm_create(gpm_handle_t* handle, int device) {
   GPM_CUDA(cudaSetDevice(device));
   gpm_handle_impl* h = new gpm_handle_impl();
   h->ev = nullptr; h->n_ev = 0; h->aux = nullptr; h->flags = nullptr;
+  // The binding creates the handle of a stream on first use, which may be inside a CUDA-graph capture; allocations
+  // are "potentially unsafe" calls under the default (global) capture mode, so this thread is switched to relaxed
+  // mode for the duration (as PyTorch's allocator does).  Nothing here enqueues work on a capturing stream.
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  const bool swapped = cudaThreadExchangeStreamCaptureMode(&mode) == cudaSuccess;
   const int rc = create_impl(h, device);
+  if (swapped) cudaThreadExchangeStreamCaptureMode(&mode);
   if (rc) destroy_impl(h);
   else *handle = reinterpret_cast<gpm_handle_t>(h);
   if (prev >= 0 && prev != device) cudaSetDevice(prev);

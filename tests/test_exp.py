@@ -1,6 +1,6 @@
 """The hand-rolled exp(x), x <= 0, of the covariance kernels (csrc/exp_neg.cuh) on the CPU: the header compiles as
 plain C with libm's fma(), every operation in it is a correctly rounded IEEE operation written out explicitly, so
-the device code computes the same bits.  Checked against mpmath (<= 0.52 ulp) and numpy (<= 1 ulp), at the underflow
+the device code computes the same bits.  All three table sizes are checked against mpmath (<= 0.56 ulp; 0.52 for the default J = 16) and numpy (<= 1 ulp), at the underflow
 edge, and for arguments large enough to wrap the integer exponent if it were not screened."""
 import ctypes
 import os
@@ -13,15 +13,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HDR = os.path.join(ROOT, "gaussianprocesspathmodelling_b200", "csrc", "exp_neg.cuh")
 
 
-@pytest.fixture(scope="module")
-def lib(tmp_path_factory):
+@pytest.fixture(scope="module", params=[4, 3, 6], ids=["J16-default", "J8", "J64"])
+def lib(tmp_path_factory, request):
     d = tmp_path_factory.mktemp("expneg")
     src = d / "shim.c"
     src.write_text(f'#include "{HDR}"\n'
                    "void v_exp_neg(const double* x, double* y, long n) { for (long i = 0; i < n; i++) y[i] = gpm_exp_neg(x[i]); }\n"
                    "void v_exp_neg_half(const double* x, double* y, long n) { for (long i = 0; i < n; i++) y[i] = gpm_exp_neg_half(x[i]); }\n")
     so = d / "shim.so"
-    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c", "-o", str(so), str(src), "-lm"], check=True)
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", f"-DGPM_EXP_LOG2J={request.param}", "-shared", "-fPIC", "-x", "c",
+                    "-o", str(so), str(src), "-lm"], check=True)
     L = ctypes.CDLL(str(so))
     for f in (L.v_exp_neg, L.v_exp_neg_half):
         f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
@@ -47,7 +48,7 @@ def test_exp_neg_within_one_ulp_of_numpy_and_half_an_ulp_of_mpmath(lib):
         for i in rng.choice(len(x), 4000, replace=False):
             t = mp.exp(mp.mpf(float(x[i])))
             worst = max(worst, float(abs(mp.mpf(float(y[i])) - t) / mp.mpf(float(np.spacing(float(t))))))
-        assert worst <= 0.52, worst
+        assert worst <= 0.56, worst          # J=16 (default): 0.52; J=8 carries a larger e^t - 1 term: 0.55
 
 
 def test_exp_neg_edges(lib):
