@@ -536,6 +536,7 @@ def run_b200(args):
         del graph
     except Exception as e:                                      # noqa: BLE001
         extra["cfg1_cuda_graph_error"] = str(e)[:200]
+        torch.cuda.set_stream(torch.cuda.default_stream())      # a failed capture leaves torch on the capture stream
 
     # ---- the other headline numbers ------------------------------------------------------------------
     if not args.no_extra:

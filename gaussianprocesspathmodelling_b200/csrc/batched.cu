@@ -1,6 +1,7 @@
 // Batched per-path fits: B independent paths of equal length N.
 //   N <= 112 (the reference's 33-point trajectories): one CTA per path, the whole fit in shared memory (small.cu).
-//   longer paths: all paths advance together through batched launches (grid.y = path) of the same kernels the
+//   112 < N <= 1024 (BASELINE config 3, N = 512): one CTA per path on the tensor cores, two paths per SM (pathfit.cu).
+//   longer paths (and the option no_path_fused): all paths advance together through batched launches (grid.y = path) of the same kernels the
 //   single-matrix path uses: covariance (lower tiles) -> blocked Cholesky -> blocked solves -> LML.
 #include <stdlib.h>
 
@@ -28,6 +29,12 @@ int launch_fit_small(const double* Xb, const double* Yb, long long B, long long 
                      const double* theta_dev, int theta_stride, double* alpha, double* lml, int* info,
                      cudaStream_t stream);
 
+bool path_fit_supported(long long N, int R);
+size_t path_fit_workspace_bytes(const gpm_handle_impl* h, long long B, long long N);
+int launch_path_fit(gpm_handle_impl* h, const double* Xb, const double* Yb, long long B, long long N, int D, int R,
+                    const Theta& th, const double* theta_host, int theta_stride, double* alpha, double* lml,
+                    int* info, void* ws, cudaStream_t st);
+
 static inline long long round_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
 
 }  // namespace gpm
@@ -38,6 +45,7 @@ extern "C" size_t gpm_fit_batched_workspace_bytes(gpm_handle_t handle, int64_t B
   if (!handle || B <= 0 || N <= 0) return 0;
   const gpm_handle_impl* h = reinterpret_cast<const gpm_handle_impl*>(handle);
   if (fit_small_supported(N) && !h->opt.no_small_fused) return (size_t)B * 8 * sizeof(double);       // one CTA per path: only per-path theta is staged
+  if (path_fit_supported(N, 1) && !h->opt.no_path_fused) return path_fit_workspace_bytes(h, B, N);   // per-CTA scratch, not per path
   const long long np = round_up_ll(N, NB);
   return (size_t)B * (size_t)(np * np + np * NB + 8 + np * 8) * sizeof(double);   // + per-path theta + z = L^{-1} Y
 }
@@ -50,8 +58,9 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
   GPM_ARG(Yb != nullptr, 3);
   gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
   const bool small = fit_small_supported(N) && !h->opt.no_small_fused;
-  GPM_ARG(B > 0 && (B <= 65535 || (small && B < (1ll << 31))), 4);   // gridDim.y / gridDim.x
-  GPM_ARG(N > 0 && B * ((N + NB - 1) / NB * NB) < (1ll << 31), 5);
+  const bool fused = !small && path_fit_supported(N, R) && !h->opt.no_path_fused;
+  GPM_ARG(B > 0 && (B <= 65535 || ((small || fused) && B < (1ll << 31))), 4);   // gridDim.y / gridDim.x
+  GPM_ARG(N > 0 && (small || fused || B * ((N + NB - 1) / NB * NB) < (1ll << 31)), 5);   // TMA row coordinates of the tiled pipeline
   Theta th;
   GPM_ARG(R >= 1 && R <= 8, 7);
   GPM_ARG(theta_stride == 0 || theta_stride == D + 2, 9);
@@ -71,6 +80,8 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
     }
     return launch_fit_small(Xb, Yb, B, N, D, R, th, tdev, (int)theta_stride, alpha, lml, info, st);
   }
+  if (fused)   // 112 < N <= 1024: one CTA per path, two paths in flight per SM, K never materialised (pathfit.cu)
+    return launch_path_fit(h, Xb, Yb, B, N, D, R, th, theta_stride ? theta : nullptr, (int)theta_stride, alpha, lml, info, ws, st);
   const long long np = round_up_ll(N, NB);
   const int nblk = (int)(np / NB);
   double* Kb = reinterpret_cast<double*>(ws);            // B stacked np x np matrices, ld = np

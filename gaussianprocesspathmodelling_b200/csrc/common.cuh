@@ -88,7 +88,7 @@ struct gpm_handle_impl {
   PFN_cuTensorMapEncodeTiled_v12000 encode;
   int* flags;                       // 2 x n_flags device ints: block-published flags of the chained solves
   int n_flags;                      //   (cleared on the stream at the start of every solve: graph-replay safe)
-  bool gemm_attr, potf2_attr, gemm_small_attr, gemm_strip_attr;       // opt-in shared-memory sizes set for this handle's device (function attributes are per device)
+  bool gemm_attr, potf2_attr, gemm_small_attr, gemm_strip_attr, pathfit_attr;       // opt-in shared-memory sizes set for this handle's device (function attributes are per device)
 };
 
 // Entry points run on the handle's device whatever the caller's current device is, and restore it on return.

@@ -16,213 +16,19 @@
 
 #include "gemm.cuh"
 
-namespace gpm {
-
-constexpr int NT8 = NB / 8;                         // 16 tiles per block edge
-constexpr int PACKED = NT8 * (NT8 + 1) / 2 * 64;    // doubles in the packed lower triangle (136 tiles)
-constexpr int POTF2_SMEM = (PACKED + 64 + NB + 4 * NB) * 8;  // 69.5 KB + 5.5 KB: three CTAs per SM (<= 75 KB each)
-
-// The 128x128 diagonal block lives in shared memory as its lower triangle of 8x8 tiles (tile (ti,tj),
-// tj <= ti, at index ti(ti+1)/2 + tj, 64 contiguous doubles, row-major).  Inside a tile the column is
-// XOR-swizzled with bit 1 of the row, which keeps every access pattern of the kernel at the minimum
-// number of shared-memory wavefronts: DMMA C fragments (128-bit, 32 lanes = 512 contiguous bytes),
-// A fragments (row g, col q) and B fragments (row q, col g) two lanes per 8-byte bank pair.
-__device__ __forceinline__ int tile_base(int ti, int tj) { return (ti * (ti + 1) / 2 + tj) * 64; }
-__device__ __forceinline__ int in_tile(int i, int c) { return (i & 7) * 8 + ((c & 7) ^ (((i >> 1) & 1) << 2)); }
-__device__ __forceinline__ int toff(int i, int c) { return tile_base(i >> 3, c >> 3) + in_tile(i, c); }
-
-// 4x4 lower Cholesky in one thread's registers (right-looking, so the serial chain per column is
-// rsqrt -> scale -> one FMA).  a: packed lower (a[i*(i+1)/2 + j]); on exit a holds L and r[j] = 1/L_jj.
-// Every loop has constant bounds with compile-time-foldable guards so the arrays stay in registers.
-// Returns the 1-based index of the first non-positive pivot (0 if none).
-__device__ __forceinline__ int chol4(double (&a)[10], double (&r)[4]) {
-  int bad = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    double d = a[j * (j + 1) / 2 + j];
-    if (!(d > 0.0) || !(d < 1.0e300)) { if (!bad) bad = j + 1; d = 1.0; }
-    r[j] = rsqrt(d);                       // 1 ulp; sqrt + divide would cost ~5x the latency on this serial path
-    a[j * (j + 1) / 2 + j] = d * r[j];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-      if (i > j) a[i * (i + 1) / 2 + j] *= r[j];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int c = 0; c < 4; c++)
-        if (i > j && c > j && c <= i)
-          a[i * (i + 1) / 2 + c] = fma(-a[i * (i + 1) / 2 + j], a[c * (c + 1) / 2 + j], a[i * (i + 1) / 2 + c]);
-  }
-  return bad;
-}
-
-// 8x8 lower Cholesky of the diagonal tile at sm[tb0..] by ONE thread, as a 2x2 blocking of 4x4 blocks:
-// factor A11, solve L21, update and factor A22.  At most 26 matrix entries are live at a time (a flat 8x8
-// keeps 36 + 8 doubles live, which no longer fits the 85-register budget of three CTAs per SM); every
-// element still sees the same sequence of operations as the flat right-looking form.  Writes L into the
-// tile and into l8 (packed), 1/L_jj into rd8.  Returns the 1-based index of the first bad pivot or 0.
-__device__ __forceinline__ int chol8_tile(double* sm, int tb0, double* l8, double* rd8) {
-  double a[10], r[4], x[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-      if (j <= i) a[i * (i + 1) / 2 + j] = sm[tb0 + in_tile(i, j)];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int c = 0; c < 4; c++) x[i][c] = sm[tb0 + in_tile(4 + i, c)];
-  int bad = chol4(a, r);
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    rd8[i] = r[i];
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-      if (j <= i) { sm[tb0 + in_tile(i, j)] = a[i * (i + 1) / 2 + j]; l8[i * (i + 1) / 2 + j] = a[i * (i + 1) / 2 + j]; }
-  }
-  // L21 = A21 * inv(L11)^T
-#pragma unroll
-  for (int c = 0; c < 4; c++)
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      double v = x[i][c];
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (k < c) v = fma(-x[i][k], a[c * (c + 1) / 2 + k], v);
-      x[i][c] = v * r[c];
-    }
-  double b[10], r2[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-      if (j <= i) b[i * (i + 1) / 2 + j] = sm[tb0 + in_tile(4 + i, 4 + j)];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      sm[tb0 + in_tile(4 + i, c)] = x[i][c];
-      l8[(4 + i) * (5 + i) / 2 + c] = x[i][c];
-    }
-  // A22 -= L21 L21^T
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (j <= i) b[i * (i + 1) / 2 + j] = fma(-x[i][k], x[j][k], b[i * (i + 1) / 2 + j]);
-  const int bad2 = chol4(b, r2);
-  if (!bad && bad2) bad = 4 + bad2;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    rd8[4 + i] = r2[i];
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-      if (j <= i) {
-        sm[tb0 + in_tile(4 + i, 4 + j)] = b[i * (i + 1) / 2 + j];
-        l8[(4 + i) * (5 + i) / 2 + 4 + j] = b[i * (i + 1) / 2 + j];
-      }
-  }
-  return bad;
-}
-
-// One level of the recursive-doubling inverse on DMMA tiles:  X21 = -X22 * (L21 * X11)  for all
-// 64/S pairs of SxS diagonal blocks (X11, X22 already inverted in place, upper parts zero).
-// Only tiles on or below the diagonal are touched (they are the only ones stored).  Each 8x8 result tile
-// is a run of DMMA pairs over its non-zero contraction tiles; the operand addresses advance by constant
-// (A) or linearly growing (B, packed rows) strides, so the inner loop is two shared loads, two DMMAs and
-// two pointer updates.  Tile (ta, tb) costs 2(TB - tb) DMMAs in phase 1 and 2(ta + 1) in phase 2, so tiles
-// are handed out in balanced pairs {(a, b), (TB-1-a, TB-1-b)} and {(a, TB-1-b), (TB-1-a, b)}.
-template <int S, int P2_WARPS>
-__device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
-  constexpr int TB = S / 8;                 // 8x8 tiles per block edge
-  constexpr int TILES = (NB / (2 * S)) * TB * TB;
-  constexpr int PER_WARP = (TILES + P2_WARPS - 1) / P2_WARPS;
-  static_assert((TB * TB) % PER_WARP == 0, "a warp's tiles must belong to one pair of blocks");
-  const int g = lane >> 2, q = lane & 3;
-  const int sw = ((g >> 1) & 1) << 2;
-  const int a_in = g * 8 + (q ^ sw);                              // A fragment: row g, col q
-  const int a4 = ((q ^ sw) ^ 4) - (q ^ sw);                       // ... col q + 4
-  const int b_in = q * 8 + (g ^ (((q >> 1) & 1) << 2));           // B fragment: row q, col g; row q + 4 is +32
-  const int c_in = g * 8 + ((2 * q) ^ sw);                        // C fragment: row g, cols 2q, 2q+1
-  double c0[PER_WARP], c1[PER_WARP];
-  int ta[PER_WARP], tb[PER_WARP];
-  const int tw = warp * PER_WARP;
-  const bool active = tw < TILES;
-  const int t1 = (active ? tw / (TB * TB) : 0) * 2 * TB;          // first tile row/column of this warp's pair
-#pragma unroll
-  for (int e = 0; e < PER_WARP; e++) {
-    const int u = (tw + e) % (TB * TB);
-    if (TB >= 2) {
-      constexpr int H = TB >= 2 ? TB / 2 : 1;
-      const int quad = u >> 2, m = u & 3, a = quad / H, b = quad % H;
-      ta[e] = (m & 1) ? TB - 1 - a : a;
-      tb[e] = (m == 1 || m == 2) ? TB - 1 - b : b;
-    } else {
-      ta[e] = 0; tb[e] = 0;
-    }
-  }
-  // phase 1: T = L21 * X11   (X11 lower: contraction tiles kt >= tb)
-  if (active) {
-#pragma unroll
-    for (int e = 0; e < PER_WARP; e++) {
-      const double* pa = sm + tile_base(t1 + TB + ta[e], t1 + tb[e]) + a_in;
-      const double* pb = sm + tile_base(t1 + tb[e], t1 + tb[e]) + b_in;
-      double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
-      for (int kt = tb[e]; kt < TB; kt++) {
-        dmma(x0, x1, pa[0], pb[0]);
-        dmma(y0, y1, pa[a4], pb[32]);
-        pa += 64;
-        pb += (t1 + kt + 1) * 64;
-      }
-      c0[e] = x0 + y0; c1[e] = x1 + y1;
-    }
-  }
-  __syncthreads();
-  if (active) {
-#pragma unroll
-    for (int e = 0; e < PER_WARP; e++)
-      *reinterpret_cast<double2*>(sm + tile_base(t1 + TB + ta[e], t1 + tb[e]) + c_in) = make_double2(c0[e], c1[e]);
-  }
-  __syncthreads();
-  // phase 2: X21 = -X22 * T   (X22 lower: contraction tiles kt <= ta)
-  if (active) {
-#pragma unroll
-    for (int e = 0; e < PER_WARP; e++) {
-      const double* pa = sm + tile_base(t1 + TB + ta[e], t1 + TB) + a_in;
-      const double* pb = sm + tile_base(t1 + TB, t1 + tb[e]) + b_in;
-      double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
-      for (int kt = 0; kt <= ta[e]; kt++) {
-        dmma(x0, x1, pa[0], pb[0]);
-        dmma(y0, y1, pa[a4], pb[32]);
-        pa += 64;
-        pb += (t1 + TB + kt + 1) * 64;
-      }
-      c0[e] = -(x0 + y0); c1[e] = -(x1 + y1);
-    }
-  }
-  __syncthreads();
-  if (active) {
-#pragma unroll
-    for (int e = 0; e < PER_WARP; e++)
-      *reinterpret_cast<double2*>(sm + tile_base(t1 + TB + ta[e], t1 + tb[e]) + c_in) = make_double2(c0[e], c1[e]);
-  }
-  __syncthreads();
-}
-
 #ifdef GPM_POTF2_TIMING
 // phase stamps of CTA 0 (cycles): the branch on a value loaded from shared memory after the barrier keeps
 // the clock read behind the barrier's completion (BAR.SYNC.DEFER_BLOCKING lets independent work issue early)
-__device__ long long g_p2_marks[64];
+namespace gpm { __device__ long long g_p2_marks[64]; }
 #define P2_MARK(slot)                                                                        \
   if (tid == 0 && blockIdx.x == 0) {                                                         \
-    const double pv_ = *reinterpret_cast<volatile double*>(sm + PACKED + 63);                \
-    if (__double_as_longlong(pv_) != 0x7ff8dead0000beefLL) g_p2_marks[slot] = clock64();     \
+    const double pv_ = *reinterpret_cast<volatile double*>(sm + gpm::PACKED + 63);           \
+    if (__double_as_longlong(pv_) != 0x7ff8dead0000beefLL) gpm::g_p2_marks[slot] = clock64(); \
   }
-#else
-#define P2_MARK(slot)
 #endif
+#include "potf2.cuh"
+
+namespace gpm {
 
 // Factor diagonal block kblk of K in shared memory, write L_kk back and inv(L_kk) to invD.
 // Rows/columns beyond N are padded with the identity.  blockIdx.x = batch index.
@@ -239,10 +45,7 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
                  int* __restrict__ info, long long batch_k, long long batch_inv,
                  const double* __restrict__ rhs_r, double* __restrict__ rhs_z, int R, long long batch_rhs_rows) {
   extern __shared__ __align__(16) double sm[];
-  double* l8 = sm + PACKED;            // [36] current 8x8 factor (packed lower)
-  double* rd = l8 + 64;                // [128] reciprocals of the diagonal of L
-  constexpr int P2_WARPS = P2_THREADS / 32;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   K += blockIdx.x * batch_k;
   invD += blockIdx.x * batch_inv + (long long)kblk * NB * NB;
   info += blockIdx.x;
@@ -273,104 +76,7 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
   __syncthreads();
   P2_MARK(1)
 
-  const int g = lane >> 2, q = lane & 3;
-  const int c_in = g * 8 + ((2 * q) ^ (((g >> 1) & 1) << 2));
-  const int x_in = g * 8 + (q ^ (((g >> 1) & 1) << 2));          // panel fragment: row g, column q
-  const int x4 = (x_in ^ 4) - x_in;                               // ... and column q + 4
-  constexpr int UW = P2_WARPS - 1;                                // update warps; warp UW looks ahead
-  if (tid == 0) {
-    const int bad = chol8_tile(sm, tile_base(0, 0), l8, rd);
-    if (bad && bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + bad));
-  }
-  __syncthreads();
-  for (int p = 0; p < 16; p++) {
-    const int c0 = 8 * p;
-    P2_MARK(2 + 3 * p)
-    // (1) panel solve by forward substitution against the factored 8x8 diagonal tile (l8, rd), one thread
-    //     per row below it:  x_c = (a_c - sum_{k<c} x_k L8[c][k]) / L8[c][c]
-    if (tid < NB && tid >= c0 + 8) {
-      double x[8];
-      double* row = sm + tile_base(tid >> 3, p) + (tid & 7) * 8;
-      const int sw = ((tid >> 1) & 1) << 2;
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        double v = row[c ^ sw];
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-          if (k < c) v = fma(-x[k], l8[c * (c + 1) / 2 + k], v);
-        x[c] = v * rd[c0 + c];
-      }
-#pragma unroll
-      for (int c = 0; c < 8; c++) row[c ^ sw] = x[c];
-    }
-    __syncthreads();
-    P2_MARK(3 + 3 * p)
-    if (p == 15) break;
-    // (2) rank-8 update of the trailing 8x8 tiles, C[ti][tj] -= X_ti X_tj^T (DMMA), with look-ahead: the last
-    //     warp updates the next diagonal tile first and factors it (one lane) while the other warps update
-    //     the remaining tiles, so the serial 8x8 factorisation leaves the critical path of the big panels.
-    const int nt = 15 - p, rbt = p + 1;
-    const int T = nt * (nt + 1) / 2;             // trailing tiles in row-major lower order; tile 0 = (rbt, rbt)
-    if (warp == UW) {
-      const double* xa = sm + tile_base(rbt, p) + x_in;
-      double2* cp = reinterpret_cast<double2*>(sm + tile_base(rbt, rbt) + c_in);
-      const double b0 = xa[0], b1 = xa[x4];
-      double2 c = *cp;
-      dmma(c.x, c.y, -b0, b0);
-      dmma(c.x, c.y, -b1, b1);
-      *cp = c;
-      __syncwarp();
-      if (lane == 0) {
-        const int bad = chol8_tile(sm, tile_base(rbt, rbt), l8, rd + c0 + 8);
-        if (bad && c0 + 8 + bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + c0 + 8 + bad));
-      }
-    } else {
-      // contiguous chunk of tiles per warp: consecutive tiles share their row, so the A fragments are
-      // reloaded only at a row change and the C / B addresses advance by constant strides
-      const int per = (T - 1 + UW - 1) / UW;
-      int t = 1 + warp * per;
-      const int tend = min(T, t + per);
-      if (t < tend) {
-        int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-        while (ti * (ti + 1) / 2 > t) ti--;
-        int tj = t - ti * (ti + 1) / 2;
-        const int bb0 = tile_base(rbt, p) + x_in;
-        int cb = tile_base(rbt + ti, rbt + tj) + c_in;      // C fragment of tile (ti, tj)
-        int bb = tile_base(rbt + tj, p) + x_in;             // B fragment: panel rows of tile-row tj
-        double a0, a1;
-        { const double* xa = sm + tile_base(rbt + ti, p) + x_in; a0 = -xa[0]; a1 = -xa[x4]; }
-        auto step = [&]() {
-          tj++; cb += 64; bb += (rbt + tj) * 64;
-          if (tj > ti) {
-            ti++; tj = 0;
-            cb = tile_base(rbt + ti, rbt) + c_in; bb = bb0;
-            const double* xa = sm + tile_base(rbt + ti, p) + x_in; a0 = -xa[0]; a1 = -xa[x4];
-          }
-        };
-        while (t < tend) {
-          const bool two = t + 1 < tend;
-          const int cbA = cb, bbA = bb;
-          const double aA0 = a0, aA1 = a1;
-          if (two) step();
-          const int cbB = cb, bbB = bb;
-          const double aB0 = a0, aB1 = a1;
-          if (t + 2 < tend) step();
-          t += 2;
-          double2 cA = *reinterpret_cast<const double2*>(sm + cbA), cB = *reinterpret_cast<const double2*>(sm + cbB);
-          const double bA0 = sm[bbA], bA1 = sm[bbA + x4], bB0 = sm[bbB], bB1 = sm[bbB + x4];
-          dmma(cA.x, cA.y, aA0, bA0);
-          dmma(cB.x, cB.y, aB0, bB0);
-          dmma(cA.x, cA.y, aA1, bA1);
-          dmma(cB.x, cB.y, aB1, bB1);
-          *reinterpret_cast<double2*>(sm + cbA) = cA;
-          if (two) *reinterpret_cast<double2*>(sm + cbB) = cB;
-        }
-      }
-    }
-    __syncthreads();
-    P2_MARK(4 + 3 * p)
-  }
+  potf2_factor<P2_THREADS, 0>(sm, tid, nv, r0, info);
 
   // ---- write L_kk (lower part, valid rows), 16-byte pairs ----
   for (int u0 = 0; u0 < NB * NB / 2 / P2_THREADS; u0 += 16) {
@@ -385,74 +91,11 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
     }
   }
   P2_MARK(50)
-  // ---- inverse, level 0: the sixteen 8x8 diagonal blocks, one thread per column ----
-  double xcol[8];
-  {
-    const int pt = tid >> 3, j = tid & 7;
-    if (tid < NB) {
-      const double* Lb = sm + tile_base(pt, pt);
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        double v = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-          if (k < i) v = fma(Lb[in_tile(i, k)], (k >= j) ? xcol[k] : 0.0, v);
-        xcol[i] = (i < j) ? 0.0 : ((i == j) ? rd[pt * 8 + i] : -v * rd[pt * 8 + i]);
-      }
-    }
-  }
-  __syncthreads();
-  if (tid < NB) {       // each column of each diagonal tile gets its inverse (zeros above the diagonal)
-    const int pt = tid >> 3, j = tid & 7;
-    double* Lb = sm + tile_base(pt, pt);
-#pragma unroll
-    for (int i = 0; i < 8; i++) Lb[in_tile(i, j)] = xcol[i];
-  }
-  __syncthreads();
-  P2_MARK(51)
-  inv_level_dmma<8, P2_WARPS>(sm, warp, lane);
-  P2_MARK(52)
-  inv_level_dmma<16, P2_WARPS>(sm, warp, lane);
-  P2_MARK(53)
-  inv_level_dmma<32, P2_WARPS>(sm, warp, lane);
-  P2_MARK(54)
-  inv_level_dmma<64, P2_WARPS>(sm, warp, lane);
+  potf2_invert<P2_THREADS, 0>(sm, tid);
   P2_MARK(55)
-  // fused forward substitution (batched fits): z_k = inv(L_kk) r_k on DMMA tiles, four right-hand sides at a
-  // time (staged in shared memory as the B operand, zero-padded to the 8 columns of a tile).  A warp owns the
-  // row tiles {w, 15 - w} (8 warps: 17 contraction tiles each) or {w} (16 warps).
-  if (rhs_r != nullptr) {
-    double* rs = rd + NB;                // [128][4]
-    const double* rk = rhs_r + (blockIdx.x * batch_rhs_rows + r0) * R;
-    double* zk = rhs_z + (blockIdx.x * batch_rhs_rows + r0) * R;
-    for (int rc = 0; rc < R; rc += 4) {
-      const int nc = min(4, R - rc);
-      for (int idx = tid; idx < NB * 4; idx += P2_THREADS) {
-        const int c = idx >> 2, j = idx & 3;
-        rs[idx] = (c < nv && j < nc) ? rk[c * R + rc + j] : 0.0;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int hh = 0; hh < 16 / P2_WARPS; hh++) {
-        const int ti = hh == 0 ? warp : 15 - warp;
-        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-        for (int kt = 0; kt <= ti; kt++) {
-          const double* ap = sm + tile_base(ti, kt) + x_in;
-          const double b0 = g < 4 ? rs[(kt * 8 + q) * 4 + g] : 0.0;
-          const double b1 = g < 4 ? rs[(kt * 8 + q + 4) * 4 + g] : 0.0;
-          dmma(c0, c1, ap[0], b0);
-          dmma(d0, d1, ap[x4], b1);
-        }
-        c0 += d0; c1 += d1;
-        const int row = ti * 8 + g;
-        if (row < nv) {
-          if (2 * q < nc) zk[row * R + rc + 2 * q] = c0;
-          if (2 * q + 1 < nc) zk[row * R + rc + 2 * q + 1] = c1;
-        }
-      }
-      __syncthreads();
-    }
-  }
+  if (rhs_r != nullptr)
+    potf2_fwd_z<P2_THREADS, 0>(sm, tid, nv, rhs_r + (blockIdx.x * batch_rhs_rows + r0) * R,
+                               rhs_z + (blockIdx.x * batch_rhs_rows + r0) * R, R);
   P2_MARK(57)
   for (int u0 = 0; u0 < NB * NB / 2 / P2_THREADS; u0 += 16) {
 #pragma unroll

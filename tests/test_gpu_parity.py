@@ -692,3 +692,43 @@ def test_two_streams_concurrent_fits_equal_the_serial_result_bitwise():
     for w, g in zip(want, got):
         for a, b in zip(w, g):
             assert torch.equal(a, b)
+
+
+def test_one_cta_per_path_tensor_core_fit():
+    """112 < N <= 1024 (BASELINE config 3): the whole fit of a path runs in one CTA -- covariance generated in
+    registers, left-looking tile updates and solves on DMMA tiles, potf2 in shared memory, both substitutions and the
+    LML (pathfit.cu).  Against the oracle and against the tiled batched pipeline (option no_path_fused), at ragged
+    sizes around the 64-row tile and 128-column block edges, with R up to 8, more paths than resident CTAs (the
+    per-CTA scratch is reused), per-path hyper-parameters and the LAPACK-style info of a singular path."""
+    rng = np.random.default_rng(17)
+    for (B, N, D, R) in ((3, 113, 2, 1), (2, 128, 3, 2), (3, 129, 2, 2), (2, 191, 3, 3), (2, 192, 2, 1), (3, 193, 2, 8),
+                         (2, 320, 3, 2), (2, 384, 2, 4), (2, 1000, 2, 2), (1, 1024, 3, 1)):
+        Xb = np.stack([wl.single_path(N, seed=900 + 7 * b + N, D=D)[0] for b in range(B)])
+        Yb = rng.standard_normal((B, N, R))
+        th = wl.default_theta(D)
+        a1, l1 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+        with _native.option("no_path_fused", 1):
+            a0, l0 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+        a_o, l_o = gp_ref.fit_batched(Xb, Yb, th)
+        assert nrm(a1.cpu().numpy(), a_o) < MEAN_TOL, (B, N, D, R)
+        assert np.abs(l1.cpu().numpy() - l_o).max() < LML_TOL * np.abs(l_o).max(), (B, N, D, R)
+        assert nrm(a1.cpu().numpy(), a0.cpu().numpy()) < 1e-10, (B, N, D, R)
+        assert np.abs((l1 - l0).cpu().numpy()).max() < 1e-11 * np.abs(l_o).max(), (B, N, D, R)
+    # more paths than resident CTAs (2 per SM): every path must equal the same path fitted alone, bit for bit
+    Xb, Yb, th = wl.batched_paths(700, 200, seed=41, D=3, R=2)
+    a, l = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+    for b in (0, 295, 296, 511, 699):
+        a1, l1 = GPmap.fit_gp_batched(Xb[b:b + 1], Yb[b:b + 1], theta=th)
+        assert torch.equal(a[b], a1[0]) and torch.equal(l[b], l1[0])
+    a_o, l_o = gp_ref.fit_batched(Xb[-2:], Yb[-2:], th)
+    assert nrm(a[-2:].cpu().numpy(), a_o) < MEAN_TOL
+    # per-path hyper-parameters
+    ths = np.stack([th * np.array([1.0 + 0.2 * b, 1.0 + 0.1 * b, 1.0 + 0.3 * b, 1.0 + 0.5 * b, 1.0 + b]) for b in range(4)])
+    a, l = GPmap.fit_gp_batched(Xb[:4], Yb[:4], theta=ths)
+    a_o, l_o = gp_ref.fit_batched(Xb[:4], Yb[:4], ths)
+    assert nrm(a.cpu().numpy(), a_o) < MEAN_TOL and np.abs(l.cpu().numpy() - l_o).max() < LML_TOL * np.abs(l_o).max()
+    # a duplicated sample with zero noise makes K singular: the path is reported, the others are unaffected
+    Xs = Xb[:3].copy(); Xs[1, 150] = Xs[1, 20]
+    th0 = th.copy(); th0[-1] = 0.0
+    with pytest.raises(np.linalg.LinAlgError, match="path 1"):
+        GPmap.fit_gp_batched(Xs, Yb[:3], theta=th0)
