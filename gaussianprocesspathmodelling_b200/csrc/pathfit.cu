@@ -62,45 +62,63 @@ struct PathFitArgs {
   double* zs;        // per CTA: Np x R  z = L^{-1} Y
 };
 
+#ifdef GPM_PATHFIT_TIMING
+// phase cycles of thread 0 of CTA 0, accumulated over its paths (instrumentation builds only)
+__device__ long long g_pf_cycles[16];
+#define PF_T(slot) if (tid == 0 && blockIdx.x == 0) { const long long now_ = clock64(); g_pf_cycles[slot] += now_ - t_last; t_last = now_; }
+#else
+#define PF_T(slot)
+#endif
+
 __device__ __forceinline__ void pf_cons_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(PF_CONS) : "memory");
 }
 
-// One slab (16 contraction steps) of a warp's 64 x 32 tile with a run-time mask of the 8 x 4 sub-tiles (bit mt*4+nt)
-// and per-column-group B offsets (the warp's sub-tile columns are not contiguous).
-__device__ __forceinline__ void pf_slab_mma(double (&acc)[8][4][2], uint32_t sa, uint32_t sb, const uint32_t (&off)[4],
-                                            const uint32_t (&boff)[4], uint32_t mask) {
+// A warp owns the 8-column sub-tile columns cset(w) = {w, 7 - w, 8 + w, 15 - w} (ascending).  One slab (16 contraction
+// steps) of its 64 x 32 tile is 8 x 4 DMMA sub-tiles per k4 step; which of them are needed is a compile-time shape
+// (mma.sync is warp-collective, so a run-time mask would put a branch around every DMMA):
+//   PF_FULL            all 32
+//   PF_COLS + n        sub-tile columns nt >= n   (solve against the lower-triangular inv(L_kk): column c needs slab s
+//                      iff 2 s <= c, and cset is ascending, so the live columns are a suffix)
+//   PF_DIAG0/1 + 2 w   half h of a diagonal block for warp w: (mt, nt) is on or below the diagonal iff cset[nt] <= mt + 8 h
+enum { PF_FULL = 0, PF_COLS = 1, PF_DIAG = 8 };
+__host__ __device__ constexpr int pf_cset(int w, int nt) { return nt == 0 ? w : (nt == 1 ? 7 - w : (nt == 2 ? 8 + w : 15 - w)); }
+template <int SHAPE>
+__host__ __device__ constexpr bool pf_live(int mt, int nt) {
+  if (SHAPE == PF_FULL) return true;
+  if (SHAPE >= PF_COLS && SHAPE < PF_DIAG) return nt >= SHAPE - PF_COLS;
+  const int w = (SHAPE - PF_DIAG) >> 1, h = (SHAPE - PF_DIAG) & 1;
+  return pf_cset(w, nt) <= mt + 8 * h;
+}
+template <int SHAPE>
+__host__ __device__ constexpr bool pf_row_live(int mt) { return pf_live<SHAPE>(mt, 0) || pf_live<SHAPE>(mt, 1) || pf_live<SHAPE>(mt, 2) || pf_live<SHAPE>(mt, 3); }
+template <int SHAPE>
+__host__ __device__ constexpr bool pf_col_live(int nt) {
+  for (int mt = 0; mt < 8; mt++) if (pf_live<SHAPE>(mt, nt)) return true;
+  return false;
+}
+
+template <int SHAPE>
+__device__ __forceinline__ void pf_slab(double (&acc)[8][4][2], uint32_t sa, uint32_t sb, const uint32_t (&off)[4],
+                                        const uint32_t (&boff)[4]) {
 #pragma unroll
   for (int k4 = 0; k4 < 4; k4++) {
     double a[8], b[4];
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++) a[mt] = lds_f64(sa + mt * 1024 + off[k4]);
+    for (int mt = 0; mt < 8; mt++)
+      if (pf_row_live<SHAPE>(mt)) a[mt] = lds_f64(sa + mt * 1024 + off[k4]);
 #pragma unroll
-    for (int nt = 0; nt < 4; nt++) b[nt] = lds_f64(sb + boff[nt] + off[k4]);
+    for (int nt = 0; nt < 4; nt++)
+      if (pf_col_live<SHAPE>(nt)) b[nt] = lds_f64(sb + boff[nt] + off[k4]);
 #pragma unroll
     for (int mt = 0; mt < 8; mt++)
 #pragma unroll
       for (int nt = 0; nt < 4; nt++)
-        if (mask >> (mt * 4 + nt) & 1u) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
-  }
-}
-__device__ __forceinline__ void pf_slab_mma_full(double (&acc)[8][4][2], uint32_t sa, uint32_t sb, const uint32_t (&off)[4],
-                                                 const uint32_t (&boff)[4]) {
-#pragma unroll
-  for (int k4 = 0; k4 < 4; k4++) {
-    double a[8], b[4];
-#pragma unroll
-    for (int mt = 0; mt < 8; mt++) a[mt] = lds_f64(sa + mt * 1024 + off[k4]);
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) b[nt] = lds_f64(sb + boff[nt] + off[k4]);
-#pragma unroll
-    for (int mt = 0; mt < 8; mt++)
-#pragma unroll
-      for (int nt = 0; nt < 4; nt++) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        if (pf_live<SHAPE>(mt, nt)) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
   }
 }
 
-template <int D>
+template <int D, int RR>
 __global__ void __launch_bounds__(PF_THREADS, 2)
 path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const __grid_constant__ CUtensorMap mapI, const PathFitArgs p) {
@@ -184,24 +202,15 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     sg++; seg_pos++;
   };
 
-  // ============================================ consumers ============================================
+  // ============================================ the path loop ============================================
   const int w = warp, g = lane >> 2, q = lane & 3;
   uint32_t off[4];
 #pragma unroll
   for (int t = 0; t < 4; t++) off[t] = frag_off(g, q, t);
-  const int cset[4] = {w, 7 - w, 8 + w, 15 - w};           // this warp's 8-column sub-tile columns
+  const int cset[4] = {w, 7 - w, 8 + w, 15 - w};           // this warp's 8-column sub-tile columns (ascending)
   uint32_t boff[4];
 #pragma unroll
   for (int nt = 0; nt < 4; nt++) boff[nt] = (uint32_t)cset[nt] * 1024u;
-  // sub-tile masks of the two halves of a diagonal block: (mt, c) is on or below the diagonal iff c <= mt + 8 h
-  uint32_t dmask[2] = {0u, 0u};
-#pragma unroll
-  for (int h = 0; h < 2; h++)
-#pragma unroll
-    for (int mt = 0; mt < 8; mt++)
-#pragma unroll
-      for (int nt = 0; nt < 4; nt++)
-        if (cset[nt] <= mt + 8 * h) dmask[h] |= 1u << (mt * 4 + nt);
 
   double* Ls = p.Ls + cta * (long long)Np * Np;
   double* invs = p.invs + cta * (long long)nblk * NB * NB;
@@ -209,6 +218,9 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   double* rs = p.rs + cta * (long long)Np * R;
   double* zs = p.zs + cta * (long long)Np * R;
 
+#ifdef GPM_PATHFIT_TIMING
+  long long t_last = clock64();
+#endif
   for (long long path = cta; path < p.B; path += gridDim.x) {
     Theta th = p.th;
     if (p.theta_dev) {
@@ -227,15 +239,7 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     for (int e = tid; e < N * R; e += PF_CONS) rs[e] = Y[e];
     double logdet = 0.0;
     pf_cons_sync();
-
-    // K(row, col) + noise on the diagonal, identity padding beyond N; same arithmetic as cov_kernel
-    auto kval = [&](int row, int col, const double* xr) -> double {
-      if (row >= N || col >= N) return row == col ? 1.0 : 0.0;
-      const double* xc = xs + col * 3;
-      double v = rbf<D>(xr, xc, th.sf2);
-      if (row == col) v += th.sn2;
-      return v;
-    };
+    PF_T(0)
 
     for (int k = 0; k < nblk; k++) {
       const int nv = min(NB, N - k * NB);
@@ -251,37 +255,77 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (live) {
           for (int s = 0; s < 8 * k; s++) {
             const uint32_t sa = slab_wait(), sb = sa + PF_A_BYTES;
-            pf_slab_mma(acc, sa, sb, off, boff, dmask[h]);
+            switch (2 * w + h) {                             // warp-uniform: the lower-triangle shape of this warp's columns
+              case 0: pf_slab<PF_DIAG + 0>(acc, sa, sb, off, boff); break;
+              case 1: pf_slab<PF_DIAG + 1>(acc, sa, sb, off, boff); break;
+              case 2: pf_slab<PF_DIAG + 2>(acc, sa, sb, off, boff); break;
+              case 3: pf_slab<PF_DIAG + 3>(acc, sa, sb, off, boff); break;
+              case 4: pf_slab<PF_DIAG + 4>(acc, sa, sb, off, boff); break;
+              case 5: pf_slab<PF_DIAG + 5>(acc, sa, sb, off, boff); break;
+              case 6: pf_slab<PF_DIAG + 6>(acc, sa, sb, off, boff); break;
+              default: pf_slab<PF_DIAG + 7>(acc, sa, sb, off, boff); break;
+            }
             slab_done();
           }
         }
         // the packed triangle's last tiles alias the first ring stage: every warp must be past its last slab
         if (h == 1) pf_cons_sync();
-#pragma unroll
+        PF_T(1)
+        // K_kk (+ noise on the diagonal, identity beyond N) at this thread's fragment positions -> packed triangle.
+        // Rolled over the sub-tile rows: 64 unrolled kernel evaluations would be 150 KB of straight-line code.
+#pragma unroll 1
         for (int mt = 0; mt < 8; mt++) {
           const int il = h * PF_HALF + mt * 8 + g;                     // row inside the block
           const int row = k * NB + il;
-          const double xr[3] = {xs[row * 3], xs[row * 3 + 1], D == 3 ? xs[row * 3 + 2] : 0.0};
+          const int rr = min(row, N - 1);
+          const double xr[3] = {xs[rr * 3], xs[rr * 3 + 1], D == 3 ? xs[rr * 3 + 2] : 0.0};
 #pragma unroll
           for (int nt = 0; nt < 4; nt++) {
-            if (!(dmask[h] >> (mt * 4 + nt) & 1u)) continue;
+            if (cset[nt] > mt + 8 * h) continue;                         // above the diagonal: not stored
             const int cl = cset[nt] * 8 + 2 * q;
             const int col = k * NB + cl;
-            const double v0 = kval(row, col, xr) - acc[mt][nt][0];
-            const double v1 = kval(row, col + 1, xr) - acc[mt][nt][1];
-            const bool pad = row >= N;
-            *reinterpret_cast<double2*>(smd + toff(il, cl)) =
-                make_double2(pad ? (il == cl ? 1.0 : 0.0) : (col >= N ? 0.0 : v0),
-                             pad ? (il == cl + 1 ? 1.0 : 0.0) : (col + 1 >= N ? 0.0 : v1));
+            double v[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int cc = col + e;
+              if (row >= N || cc >= N) { v[e] = (il == cl + e) ? 1.0 : 0.0; continue; }
+              v[e] = rbf<D>(xr, xs + cc * 3, th.sf2);
+              if (row == cc) v[e] += th.sn2;
+            }
+            *reinterpret_cast<double2*>(smd + toff(il, cl)) = make_double2(v[0], v[1]);
           }
         }
+        // ... minus the update (each thread re-reads only what it wrote itself)
+        if (k > 0) {
+#pragma unroll
+          for (int mt = 0; mt < 8; mt++) {
+            const int il = h * PF_HALF + mt * 8 + g;
+            const int row = k * NB + il;
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+              const int cl = cset[nt] * 8 + 2 * q;
+              const int col = k * NB + cl;
+              if (cset[nt] <= mt + 8 * h && row < N) {
+                double2* ptr = reinterpret_cast<double2*>(smd + toff(il, cl));
+                double2 v = *ptr;
+                if (col < N) v.x -= acc[mt][nt][0];
+                if (col + 1 < N) v.y -= acc[mt][nt][1];
+                *ptr = v;
+              }
+            }
+          }
+        }
+        PF_T(2)
       }
       pf_cons_sync();
       potf2_factor<PF_CONS, 1>(smd, tid, nv, (long long)k * NB, p.info + path);
       if (tid < nv) logdet += log(smd[toff(tid, tid)]);
       pf_cons_sync();
+      PF_T(3)
       potf2_invert<PF_CONS, 1>(smd, tid);
+      PF_T(4)
       potf2_fwd_z<PF_CONS, 1>(smd, tid, nv, rs + (long long)k * NB * R, zs + (long long)k * NB * R, R);
+      PF_T(5)
       {
         // inv(L_kk): the 8 x 8 tiles on or below the diagonal go to the scratch (the upper triangle was zeroed once)
         double* dst = invs + (long long)k * NB * NB;
@@ -297,12 +341,35 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int rows_below = N - (k + 1) * NB;
         seg_begin(1, k, rows_below > 0 ? ((rows_below + PF_HALF - 1) / PF_HALF) * (8 * k + 8) : 0);
       }
+      PF_T(6)
 
       // ------------------------------ blocks below: update, solve, forward substitution ------------------------------
       for (int i = k + 1; i < nblk; i++) {
         for (int h = 0; h < 2; h++) {
           const int row0 = i * NB + h * PF_HALF;
           if (row0 >= N) continue;
+          // K_ik at this thread's fragment positions -> R buffer, in the swizzled layout of A-operand slabs ([64 rows
+          // x 16] boxes); rolled over the sub-tile rows.  It runs while the first slabs of the tile are in flight.
+#pragma unroll 1
+          for (int mt = 0; mt < 8; mt++) {
+            const int il = mt * 8 + g;
+            const int row = row0 + il;
+            const int rr = min(row, N - 1);
+            const double xr[3] = {xs[rr * 3], xs[rr * 3 + 1], D == 3 ? xs[rr * 3 + 2] : 0.0};
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+              const int c = cset[nt];
+              const int col = k * NB + c * 8 + 2 * q;                   // < (k + 1) 128 <= row0: always a valid sample
+              double v0 = 0.0, v1 = 0.0;
+              if (row < N) {
+                v0 = rbf<D>(xr, xs + col * 3, th.sf2);
+                v1 = rbf<D>(xr, xs + (col + 1) * 3, th.sf2);
+              }
+              const uint32_t addr = rbuf + (c >> 1) * PF_A_BYTES + il * 128 + ((((c & 1) * 4 + q) ^ g) << 4);
+              asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(v0), "d"(v1) : "memory");
+            }
+          }
+          PF_T(7)
           double acc[8][4][2];
 #pragma unroll
           for (int mt = 0; mt < 8; mt++)
@@ -310,43 +377,49 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
           for (int s = 0; s < 8 * k; s++) {
             const uint32_t sa = slab_wait(), sb = sa + PF_A_BYTES;
-            pf_slab_mma_full(acc, sa, sb, off, boff);
+            pf_slab<PF_FULL>(acc, sa, sb, off, boff);
             slab_done();
           }
-          // R = K_ik - acc into the R buffer, in the swizzled layout of A-operand slabs ([64 rows x 16] boxes)
+          PF_T(8)
+          // R = K_ik - acc, in place (rows beyond N stay zero)
+          if (k > 0) {
 #pragma unroll
-          for (int mt = 0; mt < 8; mt++) {
-            const int il = mt * 8 + g;
-            const int row = row0 + il;
-            const double xr[3] = {xs[min(row, N - 1) * 3], xs[min(row, N - 1) * 3 + 1], D == 3 ? xs[min(row, N - 1) * 3 + 2] : 0.0};
+            for (int mt = 0; mt < 8; mt++) {
+              const int il = mt * 8 + g;
+              if (row0 + il < N) {
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-              const int c = cset[nt];
-              const int col = k * NB + c * 8 + 2 * q;
-              double v0 = 0.0, v1 = 0.0;
-              if (row < N) {
-                v0 = kval(row, col, xr) - acc[mt][nt][0];
-                v1 = kval(row, col + 1, xr) - acc[mt][nt][1];
+                for (int nt = 0; nt < 4; nt++) {
+                  const int c = cset[nt];
+                  const uint32_t addr = rbuf + (c >> 1) * PF_A_BYTES + il * 128 + ((((c & 1) * 4 + q) ^ g) << 4);
+                  double v0, v1;
+                  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(addr));
+                  v0 -= acc[mt][nt][0]; v1 -= acc[mt][nt][1];
+                  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(v0), "d"(v1) : "memory");
+                }
               }
-              const uint32_t addr = rbuf + (c >> 1) * PF_A_BYTES + il * 128 + ((((c & 1) * 4 + q) ^ g) << 4);
-              asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(v0), "d"(v1) : "memory");
             }
           }
           pf_cons_sync();
-          // L_ik = R inv(L_kk)^T: A from the R buffer, B = inv(L_kk) slabs; slab s is all zero for sub-tile column c > 2s+1
+          // L_ik = R inv(L_kk)^T: A from the R buffer, B = inv(L_kk) slabs; sub-tile column c needs slab s iff 2 s <= c
 #pragma unroll
           for (int mt = 0; mt < 8; mt++)
 #pragma unroll
             for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
           for (int s = 0; s < NB / SLAB_K; s++) {
             const uint32_t sa = rbuf + s * PF_A_BYTES, sb = slab_wait() + PF_A_BYTES;
-            uint32_t m4 = 0;                                // sub-tile column c needs slab s iff 16 s <= 8 c + 7
+            int dead = 0;                                   // cset is ascending: the live columns are a suffix
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++)
-              if (2 * s <= cset[nt]) m4 |= 1u << nt;
-            pf_slab_mma(acc, sa, sb, off, boff, m4 * 0x11111111u);
+            for (int nt = 0; nt < 4; nt++) dead += (cset[nt] < 2 * s) ? 1 : 0;
+            switch (dead) {
+              case 0: pf_slab<PF_COLS + 0>(acc, sa, sb, off, boff); break;
+              case 1: pf_slab<PF_COLS + 1>(acc, sa, sb, off, boff); break;
+              case 2: pf_slab<PF_COLS + 2>(acc, sa, sb, off, boff); break;
+              case 3: pf_slab<PF_COLS + 3>(acc, sa, sb, off, boff); break;
+              default: break;
+            }
             slab_done();
           }
+          PF_T(9)
           // epilogue: L_ik -> scratch (16-byte stores), partial sums of L_ik z_k per (row, warp)
 #pragma unroll
           for (int mt = 0; mt < 8; mt++) {
@@ -361,7 +434,9 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           pf_cons_sync();                                   // every warp is past its last read of the R buffer
           double* psm = smd;                                // [64][4][R] partial sums (aliases the R buffer)
           const double* zk = zs + (long long)k * NB * R;
-          for (int r = 0; r < R; r++) {
+#pragma unroll
+          for (int r = 0; r < RR; r++) {
+            if (r >= R) break;
             double zv[4][2], sum[8];
 #pragma unroll
             for (int nt = 0; nt < 4; nt++) {
@@ -395,6 +470,7 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                        (psm[(tid * 4 + 2) * R + r] + psm[(tid * 4 + 3) * R + r]);
           }
           pf_cons_sync();                                   // psm is free again (the next tile writes the R buffer)
+          PF_T(10)
         }
       }
       fence_proxy_async();                                 // this column's L tiles: generic-proxy stores, read back by TMA
@@ -403,17 +479,17 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
 
     // ------------------------------ backward substitution L^T alpha = z, alpha out, LML ------------------------------
-    pf_cons_sync();
+    PF_T(11)
     double* zsm = smd;                                      // [Np][R]
     double* ys = zsm + (long long)Np * R;                   // [128][R]
-    double* red = ys + NB * R;                              // [4][R + 1]
+    double* red = ys + NB * R;                              // [4][RR + 1]
     for (int e = tid; e < Np * R; e += PF_CONS) zsm[e] = (e / R < N) ? __ldcg(zs + e) : 0.0;
     pf_cons_sync();
     for (int i = nblk - 1; i >= 0; i--) {
       const int i0 = i * NB;
-      double accr[8];
+      double accr[RR];
 #pragma unroll
-      for (int r = 0; r < 8; r++) accr[r] = 0.0;
+      for (int r = 0; r < RR; r++) accr[r] = 0.0;
       for (int j = nblk - 1; j > i; j--) {                   // column tid of block (j, i): rows j0 .. j0+127
         const int j0 = j * NB;
         for (int rb = 0; rb < NB; rb += 32) {
@@ -427,16 +503,18 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           for (int r2 = 0; r2 < 32; r2++) {
             const double* zr = zsm + (long long)(j0 + rb + r2) * R;
 #pragma unroll
-            for (int r = 0; r < 8; r++)
+            for (int r = 0; r < RR; r++)
               if (r < R) accr[r] = fma(seg[r2], zr[r], accr[r]);
           }
         }
       }
-      for (int r = 0; r < R; r++) ys[tid * R + r] = zsm[(long long)(i0 + tid) * R + r] - accr[r];
+#pragma unroll
+      for (int r = 0; r < RR; r++)
+        if (r < R) ys[tid * R + r] = zsm[(long long)(i0 + tid) * R + r] - accr[r];
       pf_cons_sync();
       // a_i[tid] = sum_{row >= tid} inv(L_ii)[row][tid] y[row]   (inv lower triangular: rows below the column)
 #pragma unroll
-      for (int r = 0; r < 8; r++) accr[r] = 0.0;
+      for (int r = 0; r < RR; r++) accr[r] = 0.0;
       const double* Di = invs + (long long)i * NB * NB;
       for (int rb = (tid & ~31); rb < NB; rb += 32) {
         double seg[32];
@@ -446,42 +524,55 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int r2 = 0; r2 < 32; r2++) {
           const double* yr = ys + (rb + r2) * R;
 #pragma unroll
-          for (int r = 0; r < 8; r++)
+          for (int r = 0; r < RR; r++)
             if (r < R) accr[r] = fma(seg[r2], yr[r], accr[r]);
         }
       }
       pf_cons_sync();                                        // every thread has read ys and its z_i entries
-      for (int r = 0; r < R; r++) zsm[(long long)(i0 + tid) * R + r] = (i0 + tid < N) ? accr[r] : 0.0;
+#pragma unroll
+      for (int r = 0; r < RR; r++)
+        if (r < R) zsm[(long long)(i0 + tid) * R + r] = (i0 + tid < N) ? accr[r] : 0.0;
       pf_cons_sync();
     }
     // alpha out; lml[r] = -1/2 y^T alpha - sum log L_ii - N/2 log(2 pi)
-    double part[9];
+    double part[RR + 1];
 #pragma unroll
-    for (int r = 0; r < 8; r++) part[r] = 0.0;
-    part[8] = logdet;
+    for (int r = 0; r < RR; r++) part[r] = 0.0;
+    part[RR] = logdet;
     double* al = p.alpha + path * (long long)N * R;
-    for (int i = tid; i < N; i += PF_CONS)
-      for (int r = 0; r < R; r++) {
-        const double a = zsm[(long long)i * R + r];
-        al[i * R + r] = a;
-        part[r] = fma(Y[i * R + r], a, part[r]);
-      }
+    for (int i = tid; i < N; i += PF_CONS) {
+#pragma unroll
+      for (int r = 0; r < RR; r++)
+        if (r < R) {
+          const double a = zsm[(long long)i * R + r];
+          al[i * R + r] = a;
+          part[r] = fma(Y[i * R + r], a, part[r]);
+        }
+    }
     if (p.lml) {
 #pragma unroll
-      for (int r = 0; r < 9; r++) {
+      for (int r = 0; r <= RR; r++) {
         const double sv = warp_sum(part[r]);
-        if (lane == 0) red[w * 9 + r] = sv;
+        if (lane == 0) red[w * (RR + 1) + r] = sv;
       }
       pf_cons_sync();
       if (tid < R) {
         double qf = 0.0, ld = 0.0;
-        for (int ww = 0; ww < PF_CONS_WARPS; ww++) { qf += red[ww * 9 + tid]; ld += red[ww * 9 + 8]; }
+        for (int ww = 0; ww < PF_CONS_WARPS; ww++) { qf += red[ww * (RR + 1) + tid]; ld += red[ww * (RR + 1) + RR]; }
         p.lml[path * R + tid] = -0.5 * qf - ld - 0.5 * (double)N * 1.8378770664093454835606594728112;
       }
     }
     pf_cons_sync();                                          // the solve's shared memory is free for the next path
+    PF_T(12)
   }
 }
+
+#ifdef GPM_PATHFIT_TIMING
+extern "C" int gpm_debug_pathfit_cycles(long long* out, int reset) {
+  if (reset) { long long z[16] = {0}; return (int)cudaMemcpyToSymbol(g_pf_cycles, z, sizeof(z)); }
+  return (int)cudaMemcpyFromSymbol(out, g_pf_cycles, sizeof(long long) * 16);
+}
+#endif
 
 bool path_fit_supported(long long N, int R) { return N > 112 && N <= PF_MAX_N && R >= 1 && R <= 8; }
 
@@ -519,15 +610,18 @@ int launch_path_fit(gpm_handle_impl* h, const double* Xb, const double* Yb, long
   if ((rc = make_tmap(h, &mapA, Ls, ctas * np, np, np, PF_HALF))) return rc;
   if ((rc = make_tmap(h, &mapB, Ls, ctas * np, np, np, NB))) return rc;
   if ((rc = make_tmap(h, &mapI, invs, ctas * nblk * NB, NB, NB, NB))) return rc;
-  if (!h->pathfit_attr) {
-    GPM_CUDA(cudaFuncSetAttribute(path_fit_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
-    GPM_CUDA(cudaFuncSetAttribute(path_fit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
-    GPM_CUDA(cudaFuncSetAttribute(path_fit_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    GPM_CUDA(cudaFuncSetAttribute(path_fit_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    h->pathfit_attr = true;
-  }
-  if (D == 2) path_fit_kernel<2><<<(unsigned)ctas, PF_THREADS, PF_SMEM, st>>>(mapA, mapB, mapI, a);
-  else path_fit_kernel<3><<<(unsigned)ctas, PF_THREADS, PF_SMEM, st>>>(mapA, mapB, mapI, a);
+  auto launch = [&](auto kern) -> int {
+    GPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    GPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    kern<<<(unsigned)ctas, PF_THREADS, PF_SMEM, st>>>(mapA, mapB, mapI, a);
+    return 0;
+  };
+  const int RRsel = R <= 1 ? 1 : (R <= 2 ? 2 : (R <= 4 ? 4 : 8));
+  if (D == 2) rc = RRsel == 1 ? launch(path_fit_kernel<2, 1>) : RRsel == 2 ? launch(path_fit_kernel<2, 2>)
+                 : RRsel == 4 ? launch(path_fit_kernel<2, 4>) : launch(path_fit_kernel<2, 8>);
+  else rc = RRsel == 1 ? launch(path_fit_kernel<3, 1>) : RRsel == 2 ? launch(path_fit_kernel<3, 2>)
+            : RRsel == 4 ? launch(path_fit_kernel<3, 4>) : launch(path_fit_kernel<3, 8>);
+  if (rc) return rc;
   GPM_LAUNCH_CHECK();
   return 0;
 }

@@ -728,7 +728,12 @@ def test_one_cta_per_path_tensor_core_fit():
     a_o, l_o = gp_ref.fit_batched(Xb[:4], Yb[:4], ths)
     assert nrm(a.cpu().numpy(), a_o) < MEAN_TOL and np.abs(l.cpu().numpy() - l_o).max() < LML_TOL * np.abs(l_o).max()
     # a duplicated sample with zero noise makes K singular: the path is reported, the others are unaffected
-    Xs = Xb[:3].copy(); Xs[1, 150] = Xs[1, 20]
+    # half of path 1's samples duplicated with zero noise: K has rank 100, some pivot must come out non-positive;
+    # the path is reported (LAPACK-style info), the others are unaffected
+    Xs = Xb[:3].copy(); Xs[1, 100:200] = Xs[1, 0:100]
     th0 = th.copy(); th0[-1] = 0.0
     with pytest.raises(np.linalg.LinAlgError, match="path 1"):
         GPmap.fit_gp_batched(Xs, Yb[:3], theta=th0)
+    a2, _ = GPmap.fit_gp_batched(Xs, Yb[:3], theta=th0, check=False)
+    a_ok, _ = GPmap.fit_gp_batched(Xs[[0, 2]], Yb[[0, 2]], theta=th0, check=False)
+    assert torch.equal(a2[[0, 2]], a_ok)
