@@ -201,6 +201,18 @@ __device__ __forceinline__ double rbf(const double* a, const double* b, double s
   return sf2 * gpm_exp_neg_half(d2);
 }
 
+// the same with a caller-provided copy of the exp table (shared memory, gpm_exp_stage_table): bitwise the same value
+template <int D>
+__device__ __forceinline__ double rbf_t(const double* a, const double* b, double sf2, const gpm_exp_pair* tab) {
+  double dx = a[0] - b[0], dy = a[1] - b[1];
+  double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+  if (D == 3) {
+    double dz = a[2] - b[2];
+    d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
+  }
+  return sf2 * gpm_exp_neg_half_t(d2, tab);
+}
+
 // coordinates of grid point m (matches numpy.linspace: start + i*step, last point = stop exactly)
 __device__ __forceinline__ void grid_point(const gpm_grid_t& g, int64_t m, double& x, double& y) {
   int64_t iy = m / g.gx;

@@ -18,6 +18,8 @@ cov_kernel(const double* __restrict__ X, long long N, Theta th, double* __restri
            const double* __restrict__ theta_dev, int theta_stride) {
   __shared__ double xi[CT][3], xj[CT][3];
   __shared__ double tile[CT][CT_LD];
+  __shared__ gpm_exp_pair etab[GPM_EXP_J];
+  gpm_exp_stage_table(etab, threadIdx.x, 256);
   if (theta_dev) {                                  // per-path hyper-parameters: [l_1..l_D, sf2, sn2] per batch index
     const double* t = theta_dev + (long long)blockIdx.y * theta_stride;
 #pragma unroll
@@ -48,13 +50,30 @@ cov_kernel(const double* __restrict__ X, long long N, Theta th, double* __restri
   double bj0[3], bj1[3];
 #pragma unroll
   for (int d = 0; d < D; d++) { bj0[d] = xj[c2][d]; bj1[d] = xj[c2 + 1][d]; }
+  if (!diag && i0 + CT <= N && j0 + CT <= N) {
+    // interior tile (all but O(N / 64) of them): no bounds or diagonal tests, one pointer walking down the rows.  The
+    // kernel is bound by the instruction issue port, not by the FP64 pipe or HBM, so every integer instruction
+    // around the 19 FP64 ones of a kernel value counts.
+    double* dst = K + (i0 + (tid >> 5)) * ldk + j0 + c2;
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+      const int r = (tid >> 5) + 8 * p;
+      double a[3];
+#pragma unroll
+      for (int d = 0; d < D; d++) a[d] = xi[r][d];
+      const double v0 = rbf_t<D>(a, bj0, th.sf2, etab), v1 = rbf_t<D>(a, bj1, th.sf2, etab);
+      if (mirror) { tile[r][c2] = v0; tile[r][c2 + 1] = v1; }
+      *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+      dst += 8 * ldk;
+    }
+  } else
 #pragma unroll
   for (int p = 0; p < 8; p++) {
     const int r = (tid >> 5) + 8 * p;
     double a[3];
 #pragma unroll
     for (int d = 0; d < D; d++) a[d] = xi[r][d];
-    double v0 = rbf<D>(a, bj0, th.sf2), v1 = rbf<D>(a, bj1, th.sf2);
+    double v0 = rbf_t<D>(a, bj0, th.sf2, etab), v1 = rbf_t<D>(a, bj1, th.sf2, etab);
     const long long gi = i0 + r, gj = j0 + c2;
     if (gi == gj) v0 += th.sn2;
     if (gi == gj + 1) v1 += th.sn2;
@@ -84,8 +103,10 @@ cross_cov_t_kernel(const double* __restrict__ X, long long N, Theta th, const do
                    gpm_grid_t grid, int use_grid, long long m0, long long M, double* __restrict__ KsT,
                    long long ldks, long long ncols_pad) {
   __shared__ double q[32][3];
+  __shared__ gpm_exp_pair etab[GPM_EXP_J];
   const int tid = threadIdx.x;
   const long long mb = (long long)blockIdx.x * 32;          // row blocks in x: up to 2^31-1 of them
+  gpm_exp_stage_table(etab, tid, 256);
   if (tid < 32) {
     const long long m = mb + tid;
     double c[3] = {0.0, 0.0, 0.0};
@@ -99,18 +120,28 @@ cross_cov_t_kernel(const double* __restrict__ X, long long N, Theta th, const do
   __syncthreads();
   const long long i = (long long)blockIdx.y * 256 + tid;
   if (i >= ncols_pad) return;
-  double xi[3] = {0.0, 0.0, 0.0};
-  if (i < N) {
-#pragma unroll
-    for (int d = 0; d < D; d++) xi[d] = X[i * D + d] / th.l[d];
+  const int nr = (int)((M - mb) < 32 ? (M - mb) : 32);
+  double* dst = KsT + mb * ldks + i;
+  if (i >= N) {                                              // padding columns
+    for (int r = 0; r < nr; r++) dst[r * ldks] = 0.0;
+    return;
   }
-#pragma unroll 4
-  for (int r = 0; r < 32; r++) {
-    const long long m = mb + r;
-    if (m >= M) break;
-    double v = 0.0;
-    if (i < N) v = rbf<D>(q[r], xi, th.sf2);
-    KsT[m * ldks + i] = v;
+  double xi[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int d = 0; d < D; d++) xi[d] = X[i * D + d] / th.l[d];
+  if (nr == 32) {
+    // straight-line groups of eight independent evaluations (no exits inside: the chains interleave and the
+    // constants stay in registers)
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) v[r] = rbf_t<D>(q[r0 + r], xi, th.sf2, etab);
+#pragma unroll
+      for (int r = 0; r < 8; r++) dst[(r0 + r) * ldks] = v[r];
+    }
+  } else {
+    for (int r = 0; r < nr; r++) dst[r * ldks] = rbf_t<D>(q[r], xi, th.sf2, etab);
   }
 }
 
@@ -126,8 +157,10 @@ cross_cov_mean_kernel(const double* __restrict__ X, long long N, Theta th, const
                       double* __restrict__ KsT, long long ldks, long long ncols_pad, double* __restrict__ mu) {
   __shared__ double q[QR][3];
   __shared__ double red[8][QR * RR];
+  __shared__ gpm_exp_pair etab[GPM_EXP_J];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long mb = (long long)blockIdx.x * QR;
+  gpm_exp_stage_table(etab, tid, 256);
   if (tid < QR) {
     const long long m = mb + tid;
     double c[3] = {0.0, 0.0, 0.0};
@@ -160,14 +193,16 @@ cross_cov_mean_kernel(const double* __restrict__ X, long long N, Theta th, const
 #pragma unroll
       for (int k = 0; k < RR; k++) if (k < R) a[k] = alpha[i * R + k];
     }
+    // all QR evaluations first (independent chains, no branches between them), then the stores; rows beyond M read
+    // the zero coordinates staged above and are simply not stored
+    double v[QR];
+#pragma unroll
+    for (int r = 0; r < QR; r++) v[r] = in ? rbf_t<D>(qr[r], xi, th.sf2, etab) : 0.0;
 #pragma unroll
     for (int r = 0; r < QR; r++) {
-      if (mb + r < M) {
-        const double v = in ? rbf<D>(qr[r], xi, th.sf2) : 0.0;
-        KsT[(mb + r) * ldks + i] = v;
+      if (mb + r < M) KsT[(mb + r) * ldks + i] = v[r];
 #pragma unroll
-        for (int k = 0; k < RR; k++) acc[r][k] = fma(v, a[k], acc[r][k]);
-      }
+      for (int k = 0; k < RR; k++) acc[r][k] = fma(v[r], a[k], acc[r][k]);
     }
   }
 #pragma unroll
@@ -197,7 +232,9 @@ predict_mean_kernel(const double* __restrict__ X, long long N, Theta th, const d
   constexpr int CH = 512;
   __shared__ double sx[CH][3];
   __shared__ double sa[CH][RR];
+  __shared__ gpm_exp_pair etab[GPM_EXP_J];
   const int tid = threadIdx.x;
+  gpm_exp_stage_table(etab, tid, 256);
   const long long m = (long long)blockIdx.x * 256 + tid;
   double c[3] = {0.0, 0.0, 0.0};
   if (m < M) {
@@ -218,7 +255,7 @@ predict_mean_kernel(const double* __restrict__ X, long long N, Theta th, const d
     __syncthreads();
 #pragma unroll 4
     for (int i = 0; i < n; i++) {
-      const double kv = rbf<D>(qs, sx[i], th.sf2);
+      const double kv = rbf_t<D>(qs, sx[i], th.sf2, etab);
 #pragma unroll
       for (int r = 0; r < RR; r++) acc[r] = fma(kv, sa[i][r], acc[r]);
     }
