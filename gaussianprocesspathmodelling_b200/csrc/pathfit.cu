@@ -44,7 +44,8 @@ constexpr int PF_STAGE_BYTES = PF_A_BYTES + PF_B_BYTES;  // 24 KB
 constexpr int PF_R_BYTES = PF_HALF * NB * 8;             // 64 KB
 constexpr int PF_RING_OFF = PF_R_BYTES;
 constexpr int PF_BAR_OFF = PF_RING_OFF + PF_STAGES * PF_STAGE_BYTES;
-constexpr int PF_SMEM = PF_BAR_OFF + 64;
+constexpr int PF_TAB_OFF = PF_BAR_OFF + 64;                // copy of the exp table
+constexpr int PF_SMEM = PF_TAB_OFF + GPM_EXP_J * 16;
 constexpr int PF_MAX_N = 1024;
 static_assert(POTF2_DOUBLES * 8 <= PF_BAR_OFF, "potf2 workspace must fit the R buffer + ring");
 
@@ -118,6 +119,19 @@ __device__ __forceinline__ void pf_slab(double (&acc)[8][4][2], uint32_t sa, uin
   }
 }
 
+// pre-scaled coordinates of one sample / of a thread's eight fragment columns of block column col0 (clamped to N - 1)
+template <int D>
+__device__ __forceinline__ void pf_load_row(const double* xs, int row, double (&x)[3]) {
+  x[0] = xs[row * 3]; x[1] = xs[row * 3 + 1]; x[2] = D == 3 ? xs[row * 3 + 2] : 0.0;
+}
+template <int D>
+__device__ __forceinline__ void pf_load_cols(const double* xs, int col0, const int (&cset)[4], int q, int N, double (&xc)[4][2][3]) {
+#pragma unroll
+  for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) pf_load_row<D>(xs, min(col0 + cset[nt] * 8 + 2 * q + e, N - 1), xc[nt][e]);
+}
+
 template <int D, int RR>
 __global__ void __launch_bounds__(PF_THREADS, 2)
 path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -143,6 +157,8 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     fence_mbar_init();
     prefetch_tmap(&mapA); prefetch_tmap(&mapB); prefetch_tmap(&mapI);
   }
+  const gpm_exp_pair* etab = reinterpret_cast<const gpm_exp_pair*>(pf_smem + PF_TAB_OFF);
+  gpm_exp_stage_table(reinterpret_cast<gpm_exp_pair*>(pf_smem + PF_TAB_OFF), tid, PF_THREADS);
   __syncthreads();
   if ((base & 1023u) != 0) {                               // the 128-byte swizzle pattern needs a 1 KB-aligned window
     if (tid == 0 && blockIdx.x == 0) p.info[0] = -1;
@@ -232,11 +248,26 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     const double* X = p.Xb + path * (long long)N * D;
     const double* Y = p.Yb + path * (long long)N * R;
-    for (int e = tid; e < N * D; e += PF_CONS) {
-      const int i = e / D, d = e - i * D;
-      xs[i * 3 + d] = X[e] / (d == 0 ? th.l[0] : (d == 1 ? th.l[1] : th.l[2]));
+    // eight independent loads in flight per thread (xs / rs may alias X / Y as far as the compiler knows, so a plain
+    // load-store loop would pay one HBM round trip per element)
+    for (int e0 = 0; e0 < N * D; e0 += 8 * PF_CONS) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const int e = e0 + u * PF_CONS + tid; v[u] = e < N * D ? X[e] : 0.0; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int e = e0 + u * PF_CONS + tid;
+        const int i = e / D, d = e - i * D;
+        if (e < N * D) xs[i * 3 + d] = v[u] / (d == 0 ? th.l[0] : (d == 1 ? th.l[1] : th.l[2]));
+      }
     }
-    for (int e = tid; e < N * R; e += PF_CONS) rs[e] = Y[e];
+    for (int e0 = 0; e0 < N * R; e0 += 8 * PF_CONS) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const int e = e0 + u * PF_CONS + tid; v[u] = e < N * R ? Y[e] : 0.0; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const int e = e0 + u * PF_CONS + tid; if (e < N * R) rs[e] = v[u]; }
+    }
     double logdet = 0.0;
     pf_cons_sync();
     PF_T(0)
@@ -272,27 +303,35 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (h == 1) pf_cons_sync();
         PF_T(1)
         // K_kk (+ noise on the diagonal, identity beyond N) at this thread's fragment positions -> packed triangle.
-        // Rolled over the sub-tile rows: 64 unrolled kernel evaluations would be 150 KB of straight-line code.
+        // Rolled over the sub-tile rows (64 unrolled kernel evaluations would be 150 KB of straight-line code); the
+        // column coordinates are loaded once, the row coordinates one iteration ahead, the exp table sits in shared
+        // memory and the stores are plain shared-memory stores, so the (up to) eight evaluations of an iteration
+        // overlap each other's latencies.
+        {
+          double xc[4][2][3];
+          pf_load_cols<D>(xs, k * NB, cset, q, N, xc);
+          double xn[3];
+          pf_load_row<D>(xs, min(k * NB + h * PF_HALF + g, N - 1), xn);
 #pragma unroll 1
-        for (int mt = 0; mt < 8; mt++) {
-          const int il = h * PF_HALF + mt * 8 + g;                     // row inside the block
-          const int row = k * NB + il;
-          const int rr = min(row, N - 1);
-          const double xr[3] = {xs[rr * 3], xs[rr * 3 + 1], D == 3 ? xs[rr * 3 + 2] : 0.0};
+          for (int mt = 0; mt < 8; mt++) {
+            const int il = h * PF_HALF + mt * 8 + g;                     // row inside the block
+            const int row = k * NB + il;
+            const double xr[3] = {xn[0], xn[1], xn[2]};
+            if (mt < 7) pf_load_row<D>(xs, min(row + 8, N - 1), xn);
 #pragma unroll
-          for (int nt = 0; nt < 4; nt++) {
-            if (cset[nt] > mt + 8 * h) continue;                         // above the diagonal: not stored
-            const int cl = cset[nt] * 8 + 2 * q;
-            const int col = k * NB + cl;
-            double v[2];
+            for (int nt = 0; nt < 4; nt++) {
+              if (cset[nt] > mt + 8 * h) continue;                         // above the diagonal: not stored
+              const int cl = cset[nt] * 8 + 2 * q;
+              const int col = k * NB + cl;
+              double v[2];
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-              const int cc = col + e;
-              if (row >= N || cc >= N) { v[e] = (il == cl + e) ? 1.0 : 0.0; continue; }
-              v[e] = rbf<D>(xr, xs + cc * 3, th.sf2);
-              if (row == cc) v[e] += th.sn2;
+              for (int e = 0; e < 2; e++) {
+                const int cc = col + e;
+                const double kv = rbf_t<D>(xr, xc[nt][e], th.sf2, etab);
+                v[e] = (row >= N || cc >= N) ? ((il == cl + e) ? 1.0 : 0.0) : (row == cc ? kv + th.sn2 : kv);
+              }
+              *reinterpret_cast<double2*>(smd + toff(il, cl)) = make_double2(v[0], v[1]);
             }
-            *reinterpret_cast<double2*>(smd + toff(il, cl)) = make_double2(v[0], v[1]);
           }
         }
         // ... minus the update (each thread re-reads only what it wrote itself)
@@ -350,23 +389,24 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           if (row0 >= N) continue;
           // K_ik at this thread's fragment positions -> R buffer, in the swizzled layout of A-operand slabs ([64 rows
           // x 16] boxes); rolled over the sub-tile rows.  It runs while the first slabs of the tile are in flight.
+          {
+            double xc[4][2][3];
+            pf_load_cols<D>(xs, k * NB, cset, q, N, xc);
+            double xn[3];
+            pf_load_row<D>(xs, min(row0 + g, N - 1), xn);
 #pragma unroll 1
-          for (int mt = 0; mt < 8; mt++) {
-            const int il = mt * 8 + g;
-            const int row = row0 + il;
-            const int rr = min(row, N - 1);
-            const double xr[3] = {xs[rr * 3], xs[rr * 3 + 1], D == 3 ? xs[rr * 3 + 2] : 0.0};
+            for (int mt = 0; mt < 8; mt++) {
+              const int il = mt * 8 + g;
+              const int row = row0 + il;
+              const double xr[3] = {xn[0], xn[1], xn[2]};
+              if (mt < 7) pf_load_row<D>(xs, min(row + 8, N - 1), xn);
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-              const int c = cset[nt];
-              const int col = k * NB + c * 8 + 2 * q;                   // < (k + 1) 128 <= row0: always a valid sample
-              double v0 = 0.0, v1 = 0.0;
-              if (row < N) {
-                v0 = rbf<D>(xr, xs + col * 3, th.sf2);
-                v1 = rbf<D>(xr, xs + (col + 1) * 3, th.sf2);
+              for (int nt = 0; nt < 4; nt++) {
+                const int c = cset[nt];                                   // columns < (k + 1) 128 <= row0: always valid samples
+                double v0 = rbf_t<D>(xr, xc[nt][0], th.sf2, etab), v1 = rbf_t<D>(xr, xc[nt][1], th.sf2, etab);
+                if (row >= N) v0 = v1 = 0.0;
+                *reinterpret_cast<double2*>(pf_smem + (c >> 1) * PF_A_BYTES + il * 128 + ((((c & 1) * 4 + q) ^ g) << 4)) = make_double2(v0, v1);
               }
-              const uint32_t addr = rbuf + (c >> 1) * PF_A_BYTES + il * 128 + ((((c & 1) * 4 + q) ^ g) << 4);
-              asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(v0), "d"(v1) : "memory");
             }
           }
           PF_T(7)
