@@ -313,10 +313,9 @@ def fit_gp(X, Y, lengthscale=None, signal_var=1.0, noise_var=1e-2, theta=None, c
     alpha = torch.empty((N, R), dtype=torch.float64, device=X.device)
     lml_dev = torch.full((R,), float("nan"), dtype=torch.float64, device=X.device)    # stays NaN with lml=False
     th = _native.theta_array(theta)
-    _native.check(lib.gpm_cov(h, _ptr(X), N, D, th, _ptr(K), ld, _native.COV_LOWER, st), "gpm_cov")
-    _native.check(lib.gpm_potrf(h, _ptr(K), N, ld, _ptr(ws), _ptr(info), st), "gpm_potrf")
-    _native.check(lib.gpm_solve_lml(h, _ptr(K), N, ld, _ptr(ws), _ptr(Y), R, _ptr(alpha),
-                                    _ptr(lml_dev) if lml else C.c_void_p(0), st), "gpm_solve_lml")
+    # one call: covariance -> Cholesky (forward substitution riding along) -> backward substitution -> LML
+    _native.check(lib.gpm_fit(h, _ptr(X), N, D, th, _ptr(Y), R, _ptr(K), ld, _ptr(ws), _ptr(alpha),
+                              _ptr(lml_dev) if lml else C.c_void_p(0), _ptr(info), st), "gpm_fit")
     model = GPModel(X, theta, K, ws, alpha, lml_dev, info)
     if check:
         model.check()

@@ -38,6 +38,7 @@ SIGNATURES = {
     "gpm_potrf_workspace_bytes": (_sz, [_i64]),
     "gpm_potrf": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "gpm_solve_lml": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "gpm_fit": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double), _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "gpm_predict_workspace_bytes": (_sz, [_vp, _i64, _i64]),
     "gpm_predict": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double), _vp, _i64, _vp, _vp, _i32,
                               _vp, C.POINTER(GpmGrid), _i64, _i64, _vp, _vp, _vp, _sz, _i32, _vp]),

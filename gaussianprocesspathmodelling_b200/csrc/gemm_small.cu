@@ -227,6 +227,49 @@ gemm_nt_strip_kernel(const GemmArgs p) {
       else if (col < p.c_cols_end) crow[col] = v0;
     }
   }
+  if (p.rhs_r != nullptr) {
+    // fused forward substitution (single-matrix fit): r_i -= L_ik z_k with the strip still in the accumulators.  A
+    // strip holds all 128 columns of its 32 rows, so the row sums are complete inside the CTA: partial sums per
+    // (row, warp) through shared memory, added in a fixed order, one plain read-modify-write per residual entry
+    // (no other CTA of the launch touches these rows).
+    const int R = p.rhs_R;
+    double* zsm = smem_d;                        // [128][R]   z_k
+    double* psm = smem_d + NB * 8;               // [32][8][R] partial sums
+    for (int idx = tid; idx < NB * R; idx += SMALL_THREADS) zsm[idx] = p.rhs_z[p.rhs_z_row0 * R + idx];
+    __syncthreads();
+    for (int r = 0; r < R; r++) {
+      double zv[2][2], sum[4];
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) {
+        const int col = wn * 16 + nt * 8 + 2 * q;
+        zv[nt][0] = zsm[col * R + r];
+        zv[nt][1] = zsm[(col + 1) * R + r];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++) {
+        sum[mt] = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+          sum[mt] = fma(acc[mt][nt][0], zv[nt][0], sum[mt]);
+          sum[mt] = fma(acc[mt][nt][1], zv[nt][1], sum[mt]);
+        }
+        sum[mt] += __shfl_xor_sync(0xffffffffu, sum[mt], 1);
+        sum[mt] += __shfl_xor_sync(0xffffffffu, sum[mt], 2);
+        if (q == 0) psm[((mt * 8 + g) * 8 + wn) * R + r] = sum[mt];
+      }
+    }
+    __syncthreads();
+    if (tid < SR) {
+      const long long row = p.rhs_r_row0 + (long long)ti * NB + strip * SR + tid;
+      if (row < p.rhs_rows_end) {
+        double* rr = p.rhs_r + row * R;
+        const double* ps = psm + tid * 8 * R;
+        for (int r = 0; r < R; r++)
+          rr[r] -= ((ps[0 * R + r] + ps[1 * R + r]) + (ps[2 * R + r] + ps[3 * R + r])) +
+                   ((ps[4 * R + r] + ps[5 * R + r]) + (ps[6 * R + r] + ps[7 * R + r]));
+      }
+    }
+  }
 }
 
 // the output tile range overlaps the rows and columns the A operand is read from
@@ -240,7 +283,9 @@ static bool gemm_small_inplace(const GemmArgs& a) {
 // true when `args` (tile mode, one matrix) is small enough for the latency kernel and carries raw operand pointers
 bool gemm_small_eligible(const gpm_handle_impl* h, const GemmArgs& a, int batch) {
   if (h->opt.no_small_tiles || batch != 1 || a.small_A == nullptr || a.small_B == nullptr) return false;
-  if (a.sweep_nblk > 0 || a.rowsq || a.rhs_r || a.kstart_mode || a.kend_mode || a.batch_cols) return false;
+  if (a.sweep_nblk > 0 || a.rowsq || a.kstart_mode || a.kend_mode || a.batch_cols) return false;
+  // the fused forward substitution rides only on the strip kernel (a panel solve: in place, plain store, one tile column)
+  if (a.rhs_r && !(gemm_small_inplace(a) && !a.tri && a.epi == EPI_STORE && a.tiles_n == 1)) return false;
   if (a.klen % KC != 0 || (a.small_lda & 1) || (a.small_ldb & 1) || (a.a_col0 & 1) || (a.b_col0 & 1)) return false;
   // in place (the output overwrites the A operand): only the strip kernel is safe, and it handles plain
   // EPI_STORE / EPI_NEG tile columns

@@ -378,9 +378,10 @@ __device__ __forceinline__ void potf2_invert(double* sm, int tid) {
 
 // z_k = inv(L_kk) r_k with the inverse in sm: rk, zk point at row 0 of the block's right-hand sides (nv valid rows,
 // R columns, row-major).  Four right-hand sides at a time, staged in shared memory as the B operand.
+// zk may alias rk (the single-matrix fit solves in place): every entry of a four-column chunk is staged in shared
+// memory before any entry of that chunk is written.
 template <int P2_THREADS, int BAR>
-__device__ __forceinline__ void potf2_fwd_z(double* sm, int tid, int nv, const double* __restrict__ rk,
-                                            double* __restrict__ zk, int R) {
+__device__ __forceinline__ void potf2_fwd_z(double* sm, int tid, int nv, const double* rk, double* zk, int R) {
   double* rd = sm + PACKED + 64;
   constexpr int P2_WARPS = P2_THREADS / 32;
   const int warp = tid >> 5, lane = tid & 31;

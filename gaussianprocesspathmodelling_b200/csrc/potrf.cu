@@ -43,7 +43,7 @@ template <int P2_THREADS>
 __global__ void __launch_bounds__(P2_THREADS, P2_THREADS == 256 ? 3 : 1)
 potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, double* __restrict__ invD,
                  int* __restrict__ info, long long batch_k, long long batch_inv,
-                 const double* __restrict__ rhs_r, double* __restrict__ rhs_z, int R, long long batch_rhs_rows) {
+                 const double* rhs_r, double* rhs_z, int R, long long batch_rhs_rows) {   // rhs_z may alias rhs_r (solve in place)
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x;
   K += blockIdx.x * batch_k;

@@ -322,8 +322,9 @@ solve_chain_kernel(const double* __restrict__ L, long long ldl, long long N, con
 extern "C" void gpm_debug_solve_ts(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_solve_ts, sizeof(g_solve_ts)); }
 #endif
 
+// first_dir = 1: alpha already holds z = L^{-1} Y (forward substitution fused into the factorisation): backward pass only
 int solve_chain(gpm_handle_impl* h, const double* L, long long N, long long ldl, const double* invD,
-                double* alpha, int R, cudaStream_t stream) {
+                double* alpha, int R, cudaStream_t stream, int first_dir) {
   const void* fns[2];
   if (R <= 1) { fns[0] = (const void*)solve_chain_kernel<false, 1>; fns[1] = (const void*)solve_chain_kernel<true, 1>; }
   else if (R <= 2) { fns[0] = (const void*)solve_chain_kernel<false, 2>; fns[1] = (const void*)solve_chain_kernel<true, 2>; }
@@ -337,7 +338,7 @@ int solve_chain(gpm_handle_impl* h, const double* L, long long N, long long ldl,
   // flags are cleared on the stream before each direction (constant epoch), so the call sequence can be
   // captured into a CUDA graph and replayed
   GPM_CUDA(cudaMemsetAsync(h->flags, 0, 2 * (size_t)h->n_flags * sizeof(int), stream));
-  for (int dir = 0; dir < 2; dir++) {
+  for (int dir = first_dir; dir < 2; dir++) {
     int epoch = 1;
     int* flags = h->flags + dir * h->n_flags;
     void* args[] = {(void*)&L, (void*)&ldl, (void*)&N, (void*)&invD, (void*)&alpha, (void*)&R, (void*)&nblk,
@@ -548,7 +549,7 @@ extern "C" int gpm_solve_lml(gpm_handle_t h, const double* L, int64_t N, int64_t
   gpm_handle_impl* hi = reinterpret_cast<gpm_handle_impl*>(h);
   int rc = hi->opt.solve_steps
                ? solve_blocked(L, N, ldl, reinterpret_cast<const double*>(potrf_ws), alpha, R, 1, 0, 0, 0, st)
-               : solve_chain(hi, L, N, ldl, reinterpret_cast<const double*>(potrf_ws), alpha, R, st);
+               : solve_chain(hi, L, N, ldl, reinterpret_cast<const double*>(potrf_ws), alpha, R, st, 0);
   if (rc) return rc;
   if (lml) return launch_lml(L, N, ldl, Y, alpha, R, lml, 1, 0, 0, st);
   return 0;

@@ -101,6 +101,16 @@ int gpm_potrf(gpm_handle_t h, double* K, int64_t N, int64_t ldk, void* ws, int32
 int gpm_solve_lml(gpm_handle_t h, const double* L, int64_t N, int64_t ldl, const void* potrf_ws,
                   const double* Y, int32_t R, double* alpha, double* lml, gpm_stream_t stream);
 
+/* Steps 1-3 in one call (what GPmap.fit_gp issues): covariance (lower tiles) -> Cholesky -> alpha -> LML, with the
+ * forward substitution fused into the factorisation, so L is read once by the solve instead of twice.
+ * K (N x ldk, out): the factor L in its lower triangle.  ws: gpm_potrf_workspace_bytes(N) bytes, receives the inverted
+ * diagonal blocks exactly as gpm_potrf leaves them (gpm_predict / gpm_lml_grad consume them).  Y, alpha: N x R
+ * row-major, R <= 8, alpha must not alias Y.  lml: R doubles (device) or NULL.  info as in gpm_potrf.
+ * Option no_fused_solve = 1 runs the three separate steps instead (same results to rounding). */
+int gpm_fit(gpm_handle_t h, const double* X, int64_t N, int32_t D, const double* theta,
+            const double* Y, int32_t R, double* K, int64_t ldk, void* ws, double* alpha, double* lml,
+            int32_t* info, gpm_stream_t stream);
+
 /* Step 4+5.  Posterior mean and variance at query points.
  *   mu[m, r] = sum_i k(xs_m, x_i) alpha[i, r]             (fused: K* is never stored)
  *   var[m]   = max(0, signal_var - || L^{-1} k(X, xs_m) ||^2)   (blocked TRSM on FP64 tensor cores + row-norm

@@ -737,3 +737,21 @@ def test_one_cta_per_path_tensor_core_fit():
     a2, _ = GPmap.fit_gp_batched(Xs, Yb[:3], theta=th0, check=False)
     a_ok, _ = GPmap.fit_gp_batched(Xs[[0, 2]], Yb[[0, 2]], theta=th0, check=False)
     assert torch.equal(a2[[0, 2]], a_ok)
+
+
+@pytest.mark.parametrize("N,R", [(129, 1), (300, 2), (1000, 8), (2500, 2), (4173, 3), (6200, 2)])
+def test_fit_with_fused_forward_substitution_equals_the_three_step_path(N, R):
+    """gpm_fit (forward substitution riding on the factorisation: strip-kernel epilogues below ~4900 rows, the tile
+    kernel's above) against cov + potrf + two chained solves (option no_fused_solve), and the solution itself
+    against K alpha = Y.  The factor is bitwise the same; alpha differs by the summation order only."""
+    X, Y, th = wl.single_path(N, seed=N, D=2, R=R)
+    m1 = GPmap.fit_gp(X, Y, theta=th)
+    with _native.option("no_fused_solve", 1):
+        m0 = GPmap.fit_gp(X, Y, theta=th)
+    assert torch.equal(m1.L, m0.L)
+    assert nrm(m1.alpha.cpu().numpy(), m0.alpha.cpu().numpy()) < 1e-11
+    assert np.abs(m1.lml - m0.lml).max() / np.abs(m0.lml).max() < 1e-12
+    assert nrm(gp_ref.cov(X, th) @ m1.alpha.cpu().numpy(), Y.reshape(N, -1)) < 1e-9
+    # deterministic: the same call again is bitwise the same
+    m2 = GPmap.fit_gp(X, Y, theta=th)
+    assert torch.equal(m1.alpha, m2.alpha) and torch.equal(m1.lml_dev, m2.lml_dev)
