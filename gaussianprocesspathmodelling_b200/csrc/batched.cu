@@ -37,6 +37,19 @@ int launch_path_fit(gpm_handle_impl* h, const double* Xb, const double* Yb, long
 
 static inline long long round_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
 
+// 112 < N <= 1024: which of the two pipelines.  Measured on B200 (tools/ab_batched.py; 4096 x 512: tiled 12.3 ms, one
+// CTA per path 12.5 - 12.8 ms; 256 x 512: 0.99 vs 0.97 ms): the whole-batch tiled launches win by 2 - 6 % once the
+// batch is several waves of CTAs, the one-CTA-per-path kernel wins for a batch of at most one wave (2 CTAs per SM)
+// and is the only one whose scratch does not grow with the batch (per CTA, not per path: 0.7 GB instead of 8.6 GB at
+// 4096 x 512), so it also takes the batches whose tiled workspace would pass 32 GB.  Option path_fused: 0 = never,
+// 1 = this rule, 2 = always.
+static bool use_path_fit(const gpm_handle_impl* h, long long B, long long N, int R) {
+  if (!path_fit_supported(N, R) || h->opt.no_path_fused || h->opt.path_fused == 0) return false;
+  if (h->opt.path_fused >= 2) return true;
+  const long long np = round_up_ll(N, NB);
+  return B <= 2ll * h->sm_count || B > 65535 || (double)B * (double)(np * np + np * NB) * 8.0 > 32.0 * (1ull << 30);
+}
+
 }  // namespace gpm
 
 using namespace gpm;
@@ -45,7 +58,7 @@ extern "C" size_t gpm_fit_batched_workspace_bytes(gpm_handle_t handle, int64_t B
   if (!handle || B <= 0 || N <= 0) return 0;
   const gpm_handle_impl* h = reinterpret_cast<const gpm_handle_impl*>(handle);
   if (fit_small_supported(N) && !h->opt.no_small_fused) return (size_t)B * 8 * sizeof(double);       // one CTA per path: only per-path theta is staged
-  if (path_fit_supported(N, 1) && !h->opt.no_path_fused) return path_fit_workspace_bytes(h, B, N);   // per-CTA scratch, not per path
+  if (use_path_fit(h, B, N, 1)) return path_fit_workspace_bytes(h, B, N);   // per-CTA scratch, not per path
   const long long np = round_up_ll(N, NB);
   return (size_t)B * (size_t)(np * np + np * NB + 8 + np * 8) * sizeof(double);   // + per-path theta + z = L^{-1} Y
 }
@@ -58,7 +71,7 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
   GPM_ARG(Yb != nullptr, 3);
   gpm_handle_impl* h = reinterpret_cast<gpm_handle_impl*>(handle);
   const bool small = fit_small_supported(N) && !h->opt.no_small_fused;
-  const bool fused = !small && path_fit_supported(N, R) && !h->opt.no_path_fused;
+  const bool fused = !small && use_path_fit(h, B, N, R);
   GPM_ARG(B > 0 && (B <= 65535 || ((small || fused) && B < (1ll << 31))), 4);   // gridDim.y / gridDim.x
   GPM_ARG(N > 0 && (small || fused || B * ((N + NB - 1) / NB * NB) < (1ll << 31)), 5);   // TMA row coordinates of the tiled pipeline
   Theta th;

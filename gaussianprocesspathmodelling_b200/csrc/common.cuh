@@ -74,7 +74,8 @@ struct Options {
   int var_steps = 0;         // variance: one launch per block column
   int solve_steps = 0;       // solves: one launch per block step
   int grad_sweep = 0;        // gradient: inverse by a triangular sweep
-  int no_path_fused = 0;     // batched fits of 112 < N <= 1024: the tiled batched pipeline instead of one CTA per path
+  int no_path_fused = 0;     // batched fits of 112 < N <= 1024: always the tiled batched pipeline
+  int path_fused = 1;        // ... 0 = never one CTA per path, 1 = by batch size (batched.cu: use_path_fit), 2 = always
   int no_fused_solve = 0;    // single-matrix fit: separate forward substitution
 };
 

@@ -27,6 +27,7 @@
 // Shared memory: R buffer 64 KB (A-operand slabs of the solve; the packed triangle of potf2 aliases it) + a 2-stage
 // TMA ring of (8 KB A + 16 KB B) slabs = 112 KB -> two CTAs per SM.
 #include <algorithm>
+#include <type_traits>
 
 #include "gemm.cuh"
 #include "potf2.cuh"
@@ -132,6 +133,26 @@ __device__ __forceinline__ void pf_load_cols(const double* xs, int col0, const i
     for (int e = 0; e < 2; e++) pf_load_row<D>(xs, min(col0 + cset[nt] * 8 + 2 * q + e, N - 1), xc[nt][e]);
 }
 
+// One slab of the diagonal block's update C -= L_k* L_k*^T in ONE pass over the block: both operands are the same
+// [128 rows x 16] slab and only the lower triangle is needed, so warp W owns the sub-tiles (mt, nt), mt = 0..15, with
+// cset(W, nt) <= mt -- 34 of the 136 for every W -- and the B fragment of sub-tile column c is the A fragment of sub-tile
+// row c.  (Two passes over 64-row halves loaded every slab twice and left each with half the DMMAs of a full slab,
+// less than the TMA round trip the two-stage ring has to cover.)
+template <int W>
+__device__ __forceinline__ void pf_slab_diag(double (&acc)[16][4][2], uint32_t s, const uint32_t (&off)[4]) {
+#pragma unroll
+  for (int k4 = 0; k4 < 4; k4++) {
+    double a[16];
+#pragma unroll
+    for (int mt = W; mt < 16; mt++) a[mt] = lds_f64(s + mt * 1024 + off[k4]);
+#pragma unroll
+    for (int mt = W; mt < 16; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++)
+        if (pf_cset(W, nt) <= mt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], a[pf_cset(W, nt)]);
+  }
+}
+
 template <int D, int RR>
 __global__ void __launch_bounds__(PF_THREADS, 2)
 path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -168,7 +189,7 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const int inv_base = (int)(cta * nblk * NB);
 
   // ---- the slab stream.  A SEGMENT is a run of slabs with no dependency on anything the CTA still has to compute:
-  //   kind 0, column k: the update of the diagonal block, live 64-row halves t = 0, 1, 8k slabs each
+  //   kind 0, column k: the update of the diagonal block, 8k [128 x 16] slabs of L[k, :] (both operands)
   //   kind 1, column k: the blocks below, 64-row halves t = 0 .. T-1 from row (k+1) 128: 8k update slabs (A and B
   //                     from the L scratch) then 8 solve slabs (B = inv(L_kk) only; A is the R buffer)
   // Slab n of a segment goes to ring stage (global slab count) % 2.  Only thread 0 calls issue().
@@ -176,10 +197,8 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int st = gsl % PF_STAGES;
     const uint32_t dst = ring + st * PF_STAGE_BYTES, bar = bar_full + st * 8;
     if (kind == 0) {
-      const int per = 8 * k, t = n / per, sl = n - t * per;
-      mbar_arrive_expect_tx(bar, PF_STAGE_BYTES);
-      tma_load_2d(dst, &mapA, sl * SLAB_K, row_base + k * NB + t * PF_HALF, bar);
-      tma_load_2d(dst + PF_A_BYTES, &mapB, sl * SLAB_K, row_base + k * NB, bar);
+      mbar_arrive_expect_tx(bar, PF_B_BYTES);
+      tma_load_2d(dst + PF_A_BYTES, &mapB, n * SLAB_K, row_base + k * NB, bar);
     } else {
       const int per = 8 * k + 8, t = n / per, sl = n - t * per;
       if (sl < 8 * k) {
@@ -275,86 +294,66 @@ path_fit_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     for (int k = 0; k < nblk; k++) {
       const int nv = min(NB, N - k * NB);
       // ------------------------------ diagonal block: update, then potf2 ------------------------------
-      seg_begin(0, k, 8 * k * min(2, (nv + PF_HALF - 1) / PF_HALF));
-      for (int h = 0; h < 2; h++) {
-        const bool live = k * NB + h * PF_HALF < N;
-        double acc[8][4][2];
+      seg_begin(0, k, 8 * k);
+      auto diag_block = [&](auto wtag) {
+        constexpr int W = decltype(wtag)::value;
+        double acc[16][4][2];
 #pragma unroll
-        for (int mt = 0; mt < 8; mt++)
+        for (int mt = 0; mt < 16; mt++)
 #pragma unroll
           for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-        if (live) {
-          for (int s = 0; s < 8 * k; s++) {
-            const uint32_t sa = slab_wait(), sb = sa + PF_A_BYTES;
-            switch (2 * w + h) {                             // warp-uniform: the lower-triangle shape of this warp's columns
-              case 0: pf_slab<PF_DIAG + 0>(acc, sa, sb, off, boff); break;
-              case 1: pf_slab<PF_DIAG + 1>(acc, sa, sb, off, boff); break;
-              case 2: pf_slab<PF_DIAG + 2>(acc, sa, sb, off, boff); break;
-              case 3: pf_slab<PF_DIAG + 3>(acc, sa, sb, off, boff); break;
-              case 4: pf_slab<PF_DIAG + 4>(acc, sa, sb, off, boff); break;
-              case 5: pf_slab<PF_DIAG + 5>(acc, sa, sb, off, boff); break;
-              case 6: pf_slab<PF_DIAG + 6>(acc, sa, sb, off, boff); break;
-              default: pf_slab<PF_DIAG + 7>(acc, sa, sb, off, boff); break;
-            }
-            slab_done();
-          }
+        for (int s = 0; s < 8 * k; s++) {
+          const uint32_t sb = slab_wait() + PF_A_BYTES;
+          pf_slab_diag<W>(acc, sb, off);
+          slab_done();
         }
         // the packed triangle's last tiles alias the first ring stage: every warp must be past its last slab
-        if (h == 1) pf_cons_sync();
+        pf_cons_sync();
         PF_T(1)
-        // K_kk (+ noise on the diagonal, identity beyond N) at this thread's fragment positions -> packed triangle.
-        // Rolled over the sub-tile rows (64 unrolled kernel evaluations would be 150 KB of straight-line code); the
-        // column coordinates are loaded once, the row coordinates one iteration ahead, the exp table sits in shared
-        // memory and the stores are plain shared-memory stores, so the (up to) eight evaluations of an iteration
-        // overlap each other's latencies.
-        {
-          double xc[4][2][3];
-          pf_load_cols<D>(xs, k * NB, cset, q, N, xc);
-          double xn[3];
-          pf_load_row<D>(xs, min(k * NB + h * PF_HALF + g, N - 1), xn);
+        // pass 1: the update (zero for k = 0) at this thread's fragment positions of the lower triangle
+#pragma unroll
+        for (int mt = W; mt < 16; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++)
+            if (pf_cset(W, nt) <= mt)
+              *reinterpret_cast<double2*>(smd + toff(mt * 8 + g, pf_cset(W, nt) * 8 + 2 * q)) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        // pass 2: K_kk (+ noise on the diagonal, identity beyond N) minus the update, in place (each thread re-reads
+        // only what it wrote itself).  Rolled over the sub-tile rows (unrolled kernel evaluations would be > 100 KB of
+        // code); the column coordinates are loaded once, the row coordinates one iteration ahead, the exp table sits
+        // in shared memory, so the (up to) eight evaluations of an iteration overlap each other's latencies.
+        double xc[4][2][3];
+        pf_load_cols<D>(xs, k * NB, cset, q, N, xc);
+        double xn[3];
+        pf_load_row<D>(xs, min(k * NB + W * 8 + g, N - 1), xn);
 #pragma unroll 1
-          for (int mt = 0; mt < 8; mt++) {
-            const int il = h * PF_HALF + mt * 8 + g;                     // row inside the block
-            const int row = k * NB + il;
-            const double xr[3] = {xn[0], xn[1], xn[2]};
-            if (mt < 7) pf_load_row<D>(xs, min(row + 8, N - 1), xn);
+        for (int mt = W; mt < 16; mt++) {
+          const int il = mt * 8 + g;                                     // row inside the block
+          const int row = k * NB + il;
+          const double xr[3] = {xn[0], xn[1], xn[2]};
+          if (mt < 15) pf_load_row<D>(xs, min(row + 8, N - 1), xn);
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-              if (cset[nt] > mt + 8 * h) continue;                         // above the diagonal: not stored
-              const int cl = cset[nt] * 8 + 2 * q;
-              const int col = k * NB + cl;
-              double v[2];
+          for (int nt = 0; nt < 4; nt++) {
+            if (pf_cset(W, nt) > mt) continue;                           // above the diagonal: not stored
+            const int cl = pf_cset(W, nt) * 8 + 2 * q;
+            double2* ptr = reinterpret_cast<double2*>(smd + toff(il, cl));
+            const double2 u = *ptr;
+            double v[2];
 #pragma unroll
-              for (int e = 0; e < 2; e++) {
-                const int cc = col + e;
-                const double kv = rbf_t<D>(xr, xc[nt][e], th.sf2, etab);
-                v[e] = (row >= N || cc >= N) ? ((il == cl + e) ? 1.0 : 0.0) : (row == cc ? kv + th.sn2 : kv);
-              }
-              *reinterpret_cast<double2*>(smd + toff(il, cl)) = make_double2(v[0], v[1]);
+            for (int e = 0; e < 2; e++) {
+              const int cc = k * NB + cl + e;
+              const double kv = rbf_t<D>(xr, xc[nt][e], th.sf2, etab);
+              v[e] = (row >= N || cc >= N) ? ((il == cl + e) ? 1.0 : 0.0) : ((row == cc ? kv + th.sn2 : kv) - (e ? u.y : u.x));
             }
-          }
-        }
-        // ... minus the update (each thread re-reads only what it wrote itself)
-        if (k > 0) {
-#pragma unroll
-          for (int mt = 0; mt < 8; mt++) {
-            const int il = h * PF_HALF + mt * 8 + g;
-            const int row = k * NB + il;
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-              const int cl = cset[nt] * 8 + 2 * q;
-              const int col = k * NB + cl;
-              if (cset[nt] <= mt + 8 * h && row < N) {
-                double2* ptr = reinterpret_cast<double2*>(smd + toff(il, cl));
-                double2 v = *ptr;
-                if (col < N) v.x -= acc[mt][nt][0];
-                if (col + 1 < N) v.y -= acc[mt][nt][1];
-                *ptr = v;
-              }
-            }
+            *ptr = make_double2(v[0], v[1]);
           }
         }
         PF_T(2)
+      };
+      switch (w) {                                           // warp-uniform: the lower-triangle shape of this warp's columns
+        case 0: diag_block(std::integral_constant<int, 0>{}); break;
+        case 1: diag_block(std::integral_constant<int, 1>{}); break;
+        case 2: diag_block(std::integral_constant<int, 2>{}); break;
+        default: diag_block(std::integral_constant<int, 3>{}); break;
       }
       pf_cons_sync();
       potf2_factor<PF_CONS, 1>(smd, tid, nv, (long long)k * NB, p.info + path);

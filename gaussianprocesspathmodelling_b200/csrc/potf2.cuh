@@ -238,7 +238,13 @@ __device__ __forceinline__ void potf2_factor(double* sm, int tid, int nv, long l
   const int c_in = g * 8 + ((2 * q) ^ (((g >> 1) & 1) << 2));
   const int x_in = g * 8 + (q ^ (((g >> 1) & 1) << 2));          // panel fragment: row g, column q
   const int x4 = (x_in ^ 4) - x_in;                               // ... and column q + 4
-  constexpr int UW = P2_WARPS - 1;                                // update warps; warp UW looks ahead
+  constexpr int UW = P2_WARPS - 1;                                // warp UW looks ahead (factors the next diagonal tile)
+  // The look-ahead factorisation is one thread's serial chain of ~100 dependent FP64 operations, and DMMA shares the
+  // FP64 pipe of its scheduler (16 cycles per DMMA): with eight or more warps, the warps that sit on the look-ahead
+  // warp's scheduler (warp index = 3 mod 4) stay out of the rank-8 update, so that the chain never queues behind them.
+  constexpr int NU = P2_WARPS >= 8 ? P2_WARPS - P2_WARPS / 4 : UW;  // update warps
+  const bool upd_warp = P2_WARPS >= 8 ? ((warp & 3) != 3) : (warp != UW);
+  const int uidx = P2_WARPS >= 8 ? warp - (warp >> 2) : warp;
   if (tid == 0) {
     const int bad = chol8_tile(sm, tile_base(0, 0), l8, rd);
     if (bad && bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + bad));
@@ -285,11 +291,11 @@ __device__ __forceinline__ void potf2_factor(double* sm, int tid, int nv, long l
         const int bad = chol8_tile(sm, tile_base(rbt, rbt), l8, rd + c0 + 8);
         if (bad && c0 + 8 + bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + c0 + 8 + bad));
       }
-    } else {
+    } else if (upd_warp) {
       // contiguous chunk of tiles per warp: consecutive tiles share their row, so the A fragments are
       // reloaded only at a row change and the C / B addresses advance by constant strides
-      const int per = (T - 1 + UW - 1) / UW;
-      int t = 1 + warp * per;
+      const int per = (T - 1 + NU - 1) / NU;
+      int t = 1 + uidx * per;
       const int tend = min(T, t + per);
       if (t < tend) {
         int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);

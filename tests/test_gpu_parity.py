@@ -528,12 +528,14 @@ def test_run_to_run_determinism():
             assert np.array_equal(ref[4], cur[4])
 
 
-def test_config3_size_sampled_against_oracle():
-    # 4096 paths x N=512 (BASELINE config 3): every path factors (info = 0, finite LML), a strided sample of
-    # paths matches the oracle, K alpha = Y holds for the sample, and the batch is invariant to where a path sits
-    # in it (path b of the full batch == the same path fitted in a batch of 3).
+@pytest.mark.parametrize("path_fused", [1, 2], ids=["default-rule-tiled", "one-cta-per-path"])
+def test_config3_size_sampled_against_oracle(path_fused):
+    # 4096 paths x N=512 (BASELINE config 3), through both batched pipelines: every path factors (info = 0, finite
+    # LML), a strided sample of paths matches the oracle, K alpha = Y holds for the sample, and the batch is invariant
+    # to where a path sits in it (path b of the full batch == the same path fitted in a batch of 3).
     Xb, Yb, th = wl.batched_paths(4096, 512, seed=3, D=3, R=2)
-    alpha, lml = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+    with _native.option("path_fused", path_fused):
+        alpha, lml = GPmap.fit_gp_batched(Xb, Yb, theta=th)
     assert bool(torch.isfinite(lml).all()) and bool(torch.isfinite(alpha).all())
     idx = [0, 1, 777, 2048, 4095]
     a_o, l_o = gp_ref.fit_batched(Xb[idx], Yb[idx], th)
@@ -695,6 +697,23 @@ def test_two_streams_concurrent_fits_equal_the_serial_result_bitwise():
 
 
 def test_one_cta_per_path_tensor_core_fit():
+    # option path_fused = 2 forces the one-CTA-per-path kernel whatever the batch size (the default rule gives batches
+    # of more than one wave of CTAs to the tiled pipeline, which measures 2 - 6 % faster there)
+    with _native.option("path_fused", 2):
+        _one_cta_per_path_checks()
+    # the default rule: a batch within one wave takes the one-CTA-per-path kernel, a larger one the tiled pipeline
+    Xb, Yb, th = wl.batched_paths(600, 200, seed=43, D=2, R=1)
+    a, l = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+    with _native.option("no_path_fused", 1):
+        a0, l0 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+    assert torch.equal(a, a0) and torch.equal(l, l0)
+    a, l = GPmap.fit_gp_batched(Xb[:5], Yb[:5], theta=th)
+    with _native.option("path_fused", 2):
+        a2, l2 = GPmap.fit_gp_batched(Xb[:5], Yb[:5], theta=th)
+    assert torch.equal(a, a2) and torch.equal(l, l2)
+
+
+def _one_cta_per_path_checks():
     """112 < N <= 1024 (BASELINE config 3): the whole fit of a path runs in one CTA -- covariance generated in
     registers, left-looking tile updates and solves on DMMA tiles, potf2 in shared memory, both substitutions and the
     LML (pathfit.cu).  Against the oracle and against the tiled batched pipeline (option no_path_fused), at ragged

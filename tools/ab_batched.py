@@ -9,8 +9,8 @@ N = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 Xb, Yb, th = wl.batched_paths(B, N, seed=3)
 Xd, Yd = torch.from_numpy(Xb).cuda(), torch.from_numpy(Yb).cuda()
 res = {}
-for name, val in (("path_fused", 0), ("tiled", 1)):
-    with _native.option("no_path_fused", val):
+for name, val in (("path_fused", 2), ("tiled", 0)):
+    with _native.option("path_fused", val):
         for _ in range(2):
             a, l = GPmap.fit_gp_batched(Xd, Yd, theta=th, check=False)
         torch.cuda.synchronize()
