@@ -93,11 +93,13 @@ def ncu_traffic():
             s = json.load(open(os.path.join(ROOT, "profiles", name)))
             N, M = CFG["N"], CFG["G"] ** 2
             return {"bytes_per_launch": s["dram_read_bytes"] + s["dram_write_bytes"],
-                    "algorithmic_bytes_section_8d": 2.0 * 8.0 * N * M,
+                    "launches_per_step": s.get("launches_per_step", 1),
+                    "algorithmic_bytes_section_8d": 2.0 * 8.0 * N * M / s.get("launches_per_step", 1),
                     "blocked_algorithm_operand_bytes": s.get("blocked_algorithm_operand_bytes", s.get("algorithmic_operand_bytes")),
-                    "note": "the sweep re-reads W[:,0:k] for every block column k (blocked forward substitution), so its "
-                            "operand traffic is 8.6x the 2*8*N*M bytes of section 8d; at 1.2 TB/s this is far below the HBM "
-                            "roof and the kernel is DMMA-issue bound",
+                    "note": "all byte figures per launch (a step is launches_per_step chunk launches). The sweep re-reads "
+                            "W[:,0:k] for every block column k (blocked forward substitution), so its operand traffic is 8.6x "
+                            "the 2*8*N*M bytes of section 8d; at 1.2 TB/s this is far below the HBM roof and the kernel is "
+                            "DMMA-issue bound",
                     "duration_ms_under_ncu": s["duration_ms"], "dmma_pipe_active_pct": s["dmma_pipe_active_pct"],
                     "source": "profiles/" + name}
         except Exception:                                       # noqa: BLE001

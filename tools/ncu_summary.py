@@ -23,6 +23,7 @@ for r in rows[2:]:
          "sm_throughput_pct": val(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
          "fp64_pipe_active_pct": val(r, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
          "dmma_pipe_active_pct": val(r, "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active"),
+         "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
          "l2_hit_rate_pct": val(r, "lts__t_sector_hit_rate.pct"),
          "warps_active_pct": val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
          "registers_per_thread": val(r, "launch__registers_per_thread")}

@@ -15,15 +15,11 @@ a = ap.parse_args()
 X, Y, th = wl.single_path(a.n, 2, 2, 2)
 Xd, Yd = torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda()
 lib = _native.load()
-pws = None
 for s in range(a.steps):
     n0 = lib.gpm_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     m = GPmap.fit_gp(Xd, Yd, theta=th, check=False)
-    if pws is not None:
-        m._pws = pws
     mu, var = m.predict_grid(wl.BOX, (a.g, a.g))
     e1.record(); torch.cuda.synchronize()
-    pws = m._pws
     print(f"step {s}: {e0.elapsed_time(e1):.3f} ms, {lib.gpm_launch_count() - n0} library launches, info={int(m.info.item())}")
