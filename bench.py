@@ -294,6 +294,22 @@ def timed(torch, fn, reps, warm=1, flush=None):
     return tot / reps
 
 
+def timed_pair(torch, fa, fb, reps, flush=None):
+    """Median CUDA-event times (ms) of two functions measured alternately (a, b, a, b, ...): a difference of the two
+    is then free of the drift between two separate timing loops."""
+    fa(); fb()
+    torch.cuda.synchronize()
+    ta, tb = [], []
+    for _ in range(reps):
+        for f, acc in ((fa, ta), (fb, tb)):
+            if flush is not None:
+                flush()
+            e0, e1 = ev_pair(torch)
+            e0.record(); f(); e1.record(); e1.synchronize()
+            acc.append(e0.elapsed_time(e1))
+    return float(np.median(ta)), float(np.median(tb))
+
+
 def run_b200(args):
     import ctypes as C
     import torch
@@ -458,9 +474,11 @@ def run_b200(args):
 
     def k_fit():
         _native.check(lib.gpm_fit(h, ptr(Xd), N, D, tha, ptr(Yd), R, ptr(K), ld, ptr(ws), ptr(alpha), ptr(lml), ptr(infod), st), "fit")
-    phases["fit_fused_ms"] = timed(torch, k_fit, 5, flush=flush)             # gpm_fit: what GPmap.fit_gp issues
-    # the solve's share of the fused fit (forward substitution rides on the factorisation; backward chain + LML after it)
-    phases["solve_lml_ms"] = phases["fit_fused_ms"] - t_cp
+    # the solve's share of the fused fit (forward substitution rides on the factorisation; the backward chain, which
+    # also produces the LML, after it): gpm_fit against covariance + factorisation, measured alternately, medians of 15
+    t_cp_i, t_fit_i = timed_pair(torch, cov_potrf, k_fit, 15, flush=flush)
+    phases["fit_fused_ms"] = t_fit_i                                         # gpm_fit: what GPmap.fit_gp issues
+    phases["solve_lml_ms"] = t_fit_i - t_cp_i
     nl0 = lib.gpm_launch_count()
     phases["predict_var_ms"] = timed(torch, lambda: k_pred(2), 2, warm=1)
     var_launches = (lib.gpm_launch_count() - nl0) // 3
@@ -575,17 +593,17 @@ def run_b200(args):
         y4 = torch.from_numpy(Y4).to(dev); a4 = torch.empty_like(y4); l4 = torch.empty(1, dtype=torch.float64, device=dev)
         t_solve4 = timed(torch, lambda: _native.check(lib.gpm_solve_lml(h, ptr(K4), N4, N4, ptr(ws4), ptr(y4), 1, ptr(a4), ptr(l4), st), "solve"), 3, flush=flush)
         t_fit4 = timed(torch, lambda: GPmap.fit_gp(X4d, y4, theta=th4, check=False), 3, flush=flush)
-        t_fused4 = timed(torch, lambda: _native.check(lib.gpm_fit(h, ptr(X4d), N4, 2, th4a, ptr(y4), 1, ptr(K4), N4, ptr(ws4), ptr(a4), ptr(l4), ptr(infod), st), "fit"), 3, flush=flush)
+        t_cp4_i, t_fused4 = timed_pair(torch, cp4, lambda: _native.check(lib.gpm_fit(h, ptr(X4d), N4, 2, th4a, ptr(y4), 1, ptr(K4), N4, ptr(ws4), ptr(a4), ptr(l4), ptr(infod), st), "fit"), 5, flush=flush)
         extra["cfg4_N16384"] = {
             "cov_ms": t_cov4, "cov_gbs": 8.0 * N4 * N4 / (t_cov4 * 1e-3) / 1e9, "cov_frac_hbm": 8.0 * N4 * N4 / (t_cov4 * 1e-3) / 1e9 / peaks["hbm_gbs"],
             "cov_lower_ms": t_cov4l,
             "potrf_ms": t_potrf4, "potrf_tflops": N4 ** 3 / 3 / (t_potrf4 * 1e-3) / 1e12,
             "potrf_frac_dgemm": N4 ** 3 / 3 / (t_potrf4 * 1e-3) / 1e12 / peaks["fp64_tflops"],
             "solve_lml_3step_ms": t_solve4, "fit_fused_ms": t_fused4,
-            # the solve's share of the fused fit: gpm_fit minus (covariance + factorisation); its algorithmic traffic
+            # the solve's share of the fused fit: gpm_fit minus (covariance + factorisation), measured alternately; its algorithmic traffic
             # is one pass over the lower triangle of L (4 N^2 bytes) since the forward pass rides on the factorisation
-            "solve_lml_ms": t_fused4 - t_cp4, "solve_gbs": 4.0 * N4 * N4 / (max(t_fused4 - t_cp4, 1e-6) * 1e-3) / 1e9,
-            "solve_frac_hbm": 4.0 * N4 * N4 / (max(t_fused4 - t_cp4, 1e-6) * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "solve_lml_ms": t_fused4 - t_cp4_i, "solve_gbs": 4.0 * N4 * N4 / (max(t_fused4 - t_cp4_i, 1e-6) * 1e-3) / 1e9,
+            "solve_frac_hbm": 4.0 * N4 * N4 / (max(t_fused4 - t_cp4_i, 1e-6) * 1e-3) / 1e9 / peaks["hbm_gbs"],
             "fit_gp_total_ms": t_fit4,
             "info": int(infod.item()),
         }

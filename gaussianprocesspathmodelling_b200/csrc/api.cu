@@ -135,7 +135,8 @@ static int create_impl(gpm_handle_impl* h, int device) {
   h->n_flags = 8192;                  // up to N = 2^20
   // (no memset here: every solve clears the flags on its own stream, and a synchronous memset would invalidate a
   //  CUDA-graph capture in progress -- the Python binding creates the handle of a new stream on first use)
-  GPM_CUDA(cudaMalloc(&h->flags, 2 * h->n_flags * sizeof(int)));
+  GPM_CUDA(cudaMalloc(&h->flags, 3 * h->n_flags * sizeof(int)));
+  GPM_CUDA(cudaMalloc(&h->lml_part, (size_t)h->n_flags * 9 * sizeof(double)));
   return 0;
 }
 
@@ -144,6 +145,7 @@ static void destroy_impl(gpm_handle_impl* h) {
   delete[] h->ev;
   if (h->aux) cudaStreamDestroy(h->aux);
   if (h->flags) cudaFree(h->flags);
+  if (h->lml_part) cudaFree(h->lml_part);
   delete h;
 }
 
@@ -160,7 +162,7 @@ int gpm_create(gpm_handle_t* handle, int device) {
   GPM_CUDA(cudaGetDevice(&prev));
   GPM_CUDA(cudaSetDevice(device));
   gpm_handle_impl* h = new gpm_handle_impl();
-  h->ev = nullptr; h->n_ev = 0; h->aux = nullptr; h->flags = nullptr;
+  h->ev = nullptr; h->n_ev = 0; h->aux = nullptr; h->flags = nullptr; h->lml_part = nullptr;
   // The binding creates the handle of a stream on first use, which may be inside a CUDA-graph capture; allocations
   // are "potentially unsafe" calls under the default (global) capture mode, so this thread is switched to relaxed
   // mode for the duration (as PyTorch's allocator does).  Nothing here enqueues work on a capturing stream.

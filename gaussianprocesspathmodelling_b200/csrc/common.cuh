@@ -88,7 +88,9 @@ struct gpm_handle_impl {
   int n_ev;
   PFN_cuTensorMapEncodeTiled_v12000 encode;
   int* flags;                       // 2 x n_flags device ints: block-published flags of the chained solves
-  int n_flags;                      //   (cleared on the stream at the start of every solve: graph-replay safe)
+  int n_flags;                      //   (cleared on the stream at the start of every solve: graph-replay safe); a third
+                                    //   array of n_flags publishes the per-block LML shares of the backward pass
+  double* lml_part;                 // n_flags x 9 doubles: per-block shares of the log marginal likelihood
   bool gemm_attr, potf2_attr, gemm_small_attr, gemm_strip_attr, pathfit_attr;       // opt-in shared-memory sizes set for this handle's device (function attributes are per device)
 };
 

@@ -14,7 +14,7 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
                   int batch, long long batch_rows, cudaStream_t s0, double* rhs_r, double* rhs_z, int R,
                   long long batch_rhs_rows);
 int solve_chain(gpm_handle_impl* h, const double* L, long long N, long long ldl, const double* invD,
-                double* alpha, int R, cudaStream_t stream, int first_dir);
+                double* alpha, int R, cudaStream_t stream, int first_dir, const double* Y, double* lml);
 int solve_blocked(const double* L, long long N, long long ldl, const double* invD, double* alpha, int R,
                   int batch, long long batch_l, long long batch_inv, long long batch_z, cudaStream_t stream);
 int launch_lml(const double* L, long long N, long long ldl, const double* Y, const double* alpha, int R,
@@ -50,13 +50,13 @@ extern "C" int gpm_fit(gpm_handle_t handle, const double* X, int64_t N, int32_t 
   if (h->opt.no_fused_solve || h->opt.solve_steps) {
     if ((rc = potrf_blocked(h, K, N, ldk, invD, info, 1, 0, st, nullptr, nullptr, 0, 0))) return rc;
     rc = h->opt.solve_steps ? solve_blocked(K, N, ldk, invD, alpha, R, 1, 0, 0, 0, st)
-                            : solve_chain(h, K, N, ldk, invD, alpha, R, st, 0);
+                            : solve_chain(h, K, N, ldk, invD, alpha, R, st, 0, Y, lml);
   } else {
     // alpha enters as the running residual and is overwritten block by block with z = L^{-1} Y
     if ((rc = potrf_blocked(h, K, N, ldk, invD, info, 1, 0, st, alpha, alpha, R, N))) return rc;
-    rc = solve_chain(h, K, N, ldk, invD, alpha, R, st, 1);
+    rc = solve_chain(h, K, N, ldk, invD, alpha, R, st, 1, Y, lml);    // the LML comes out of the backward pass
   }
   if (rc) return rc;
-  if (lml) return launch_lml(K, N, ldk, Y, alpha, R, lml, 1, 0, 0, st);
+  if (lml && h->opt.solve_steps) return launch_lml(K, N, ldk, Y, alpha, R, lml, 1, 0, 0, st);
   return 0;
 }

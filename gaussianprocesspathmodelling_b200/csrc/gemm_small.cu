@@ -185,6 +185,21 @@ gemm_nt_strip_kernel(const GemmArgs p) {
 #pragma unroll
     for (int nt = 0; nt < 2; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
+  // fused forward substitution: z_k (128 x R, written by potf2 before this launch) and this strip's residual rows are
+  // fetched now, so that their latency hides behind the main loop instead of following it on the critical path
+  double zpre[4] = {0.0, 0.0, 0.0, 0.0}, rpre[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const long long rhs_row = p.rhs_r_row0 + (long long)ti * NB + strip * SR + tid;
+  if (p.rhs_r != nullptr) {
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (tid + SMALL_THREADS * u < NB * p.rhs_R) zpre[u] = p.rhs_z[p.rhs_z_row0 * p.rhs_R + tid + SMALL_THREADS * u];
+    if (tid < SR && rhs_row < p.rhs_rows_end) {
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        if (r < p.rhs_R) rpre[r] = p.rhs_r[rhs_row * p.rhs_R + r];
+    }
+  }
+
   if (nchunk > 0) stage(0, 0);
   for (int c = 0; c < nchunk; c++) {
     if (c + 1 < nchunk) { stage(c + 1, (c + 1) & 1); cp_async_wait<1>(); }
@@ -235,7 +250,9 @@ gemm_nt_strip_kernel(const GemmArgs p) {
     const int R = p.rhs_R;
     double* zsm = smem_d;                        // [128][R]   z_k
     double* psm = smem_d + NB * 8;               // [32][8][R] partial sums
-    for (int idx = tid; idx < NB * R; idx += SMALL_THREADS) zsm[idx] = p.rhs_z[p.rhs_z_row0 * R + idx];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (tid + SMALL_THREADS * u < NB * R) zsm[tid + SMALL_THREADS * u] = zpre[u];
     __syncthreads();
     for (int r = 0; r < R; r++) {
       double zv[2][2], sum[4];
@@ -259,15 +276,14 @@ gemm_nt_strip_kernel(const GemmArgs p) {
       }
     }
     __syncthreads();
-    if (tid < SR) {
-      const long long row = p.rhs_r_row0 + (long long)ti * NB + strip * SR + tid;
-      if (row < p.rhs_rows_end) {
-        double* rr = p.rhs_r + row * R;
-        const double* ps = psm + tid * 8 * R;
-        for (int r = 0; r < R; r++)
-          rr[r] -= ((ps[0 * R + r] + ps[1 * R + r]) + (ps[2 * R + r] + ps[3 * R + r])) +
-                   ((ps[4 * R + r] + ps[5 * R + r]) + (ps[6 * R + r] + ps[7 * R + r]));
-      }
+    if (tid < SR && rhs_row < p.rhs_rows_end) {
+      double* rr = p.rhs_r + rhs_row * R;
+      const double* ps = psm + tid * 8 * R;
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        if (r < R)
+          rr[r] = rpre[r] - (((ps[0 * R + r] + ps[1 * R + r]) + (ps[2 * R + r] + ps[3 * R + r])) +
+                             ((ps[4 * R + r] + ps[5 * R + r]) + (ps[6 * R + r] + ps[7 * R + r])));
     }
   }
 }

@@ -386,7 +386,19 @@ __device__ __forceinline__ void potf2_invert(double* sm, int tid) {
 // R columns, row-major).  Four right-hand sides at a time, staged in shared memory as the B operand.
 // zk may alias rk (the single-matrix fit solves in place): every entry of a four-column chunk is staged in shared
 // memory before any entry of that chunk is written.
-template <int P2_THREADS, int BAR>
+// The first chunk of right-hand sides into the stage (no barrier): callers whose r_k is final before the
+// factorisation starts call this early, so that the global-load latency hides behind the factorisation.
+template <int P2_THREADS>
+__device__ __forceinline__ void potf2_stage_rhs(double* sm, int tid, int nv, const double* rk, int R) {
+  double* rs = sm + PACKED + 64 + NB;           // = rd + NB (potf2_fwd_z)
+  const int nc = min(4, R);
+  for (int idx = tid; idx < NB * 4; idx += P2_THREADS) {
+    const int c = idx >> 2, j = idx & 3;
+    rs[idx] = (c < nv && j < nc) ? rk[c * R + j] : 0.0;
+  }
+}
+
+template <int P2_THREADS, int BAR, bool STAGED = false>
 __device__ __forceinline__ void potf2_fwd_z(double* sm, int tid, int nv, const double* rk, double* zk, int R) {
   double* rd = sm + PACKED + 64;
   constexpr int P2_WARPS = P2_THREADS / 32;
@@ -401,9 +413,11 @@ __device__ __forceinline__ void potf2_fwd_z(double* sm, int tid, int nv, const d
     double* rs = rd + NB;                // [128][4]
     for (int rc = 0; rc < R; rc += 4) {
       const int nc = min(4, R - rc);
-      for (int idx = tid; idx < NB * 4; idx += P2_THREADS) {
-        const int c = idx >> 2, j = idx & 3;
-        rs[idx] = (c < nv && j < nc) ? rk[c * R + rc + j] : 0.0;
+      if (!(STAGED && rc == 0)) {
+        for (int idx = tid; idx < NB * 4; idx += P2_THREADS) {
+          const int c = idx >> 2, j = idx & 3;
+          rs[idx] = (c < nv && j < nc) ? rk[c * R + rc + j] : 0.0;
+        }
       }
       p2_sync<P2_THREADS, BAR>();
 #pragma unroll

@@ -72,6 +72,8 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
       if ((c >> 3) <= (i >> 3)) *reinterpret_cast<double2*>(sm + toff(i, c)) = v[u];
     }
   }
+  if (rhs_r != nullptr)     // r_k is final before this launch: stage it now, its latency hides behind the factorisation
+    potf2_stage_rhs<P2_THREADS>(sm, tid, nv, rhs_r + (blockIdx.x * batch_rhs_rows + r0) * R, R);
   P2_MARK(0)
   __syncthreads();
   P2_MARK(1)
@@ -94,7 +96,7 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
   potf2_invert<P2_THREADS, 0>(sm, tid);
   P2_MARK(55)
   if (rhs_r != nullptr)
-    potf2_fwd_z<P2_THREADS, 0>(sm, tid, nv, rhs_r + (blockIdx.x * batch_rhs_rows + r0) * R,
+    potf2_fwd_z<P2_THREADS, 0, true>(sm, tid, nv, rhs_r + (blockIdx.x * batch_rhs_rows + r0) * R,
                                rhs_z + (blockIdx.x * batch_rhs_rows + r0) * R, R);
   P2_MARK(57)
   for (int u0 = 0; u0 < NB * NB / 2 / P2_THREADS; u0 += 16) {

@@ -215,7 +215,8 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 template <bool BWD, int RR>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 solve_chain_kernel(const double* __restrict__ L, long long ldl, long long N, const double* __restrict__ invD,
-                   double* z, int R, int nblk, int* flags, int epoch) {
+                   double* z, int R, int nblk, int* flags, int epoch,
+                   const double* __restrict__ Yl, double* lml_part, int* lml_flags, double* lml_out) {
   extern __shared__ double csm[];
   double* sinv = csm;                       // [128][ILD]  inverse of this block's diagonal block
   double* zs = sinv + NB * ILD;             // [128][RR] the dependency block just received
@@ -300,14 +301,19 @@ solve_chain_kernel(const double* __restrict__ L, long long ldl, long long N, con
     for (int r = 0; r < RR; r++) part[(qd * NB + e) * RR + r] = acc[r];
     __syncthreads();
     ST_MARK(6, i)                                  // inverse-block product done
+    double aval[RR];
+#pragma unroll
+    for (int r = 0; r < RR; r++) aval[r] = 0.0;
     if (tid < NB) {
       const long long gr = i0 + tid;
       if (gr < N) {
 #pragma unroll
         for (int r = 0; r < RR; r++) {
-          if (r < R)
-            z[gr * R + r] = (part[(0 * NB + tid) * RR + r] + part[(1 * NB + tid) * RR + r]) +
-                            (part[(2 * NB + tid) * RR + r] + part[(3 * NB + tid) * RR + r]);
+          if (r < R) {
+            aval[r] = (part[(0 * NB + tid) * RR + r] + part[(1 * NB + tid) * RR + r]) +
+                      (part[(2 * NB + tid) * RR + r] + part[(3 * NB + tid) * RR + r]);
+            z[gr * R + r] = aval[r];
+          }
         }
       }
     }
@@ -315,6 +321,59 @@ solve_chain_kernel(const double* __restrict__ L, long long ldl, long long N, con
     ST_MARK(7, i)                                  // z stored
     if (tid == 0) { __threadfence(); flag_set(flags + i, epoch); }
     ST_MARK(2, i)                                 // published
+    if (BWD && lml_out != nullptr) {
+      // Log marginal likelihood folded into the backward pass (off the chain: after the block is published).  Each
+      // block leaves its share  sum_rows Y alpha  and  sum_rows log L_ii = -sum log inv(L_ii)_ii  in lml_part and
+      // raises a second flag; the owner of block 0 -- the last block of the pass -- adds the shares in block order.
+      double v[RR + 1];
+#pragma unroll
+      for (int r = 0; r <= RR; r++) v[r] = 0.0;
+      if (tid < NB && i0 + tid < N) {
+#pragma unroll
+        for (int r = 0; r < RR; r++)
+          if (r < R) v[r] = Yl[(i0 + tid) * R + r] * aval[r];
+        v[RR] = -log(sinv[tid * ILD + tid]);
+      }
+      if (tid < NB) {
+#pragma unroll
+        for (int r = 0; r <= RR; r++) {
+          const double sv = warp_sum(v[r]);
+          if ((tid & 31) == 0) part[(tid >> 5) * (RR + 1) + r] = sv;
+        }
+      }
+      __syncthreads();
+      if (tid <= RR) {
+        const double sv = (part[0 * (RR + 1) + tid] + part[1 * (RR + 1) + tid]) + (part[2 * (RR + 1) + tid] + part[3 * (RR + 1) + tid]);
+        lml_part[(long long)i * (RMAX + 1) + (tid == RR ? RMAX : tid)] = sv;
+      }
+      __syncthreads();
+      if (tid == 0) { __threadfence(); flag_set(lml_flags + i, epoch); }
+      if (i == 0) {
+        for (int j = 1 + tid; j < nblk; j += CH_THREADS) flag_wait(lml_flags + j, epoch);
+        __syncthreads();
+        // thread t adds the shares of blocks t, t + 128, ... in increasing order; then a fixed-order combine
+        if (tid < NB) {
+#pragma unroll
+          for (int r = 0; r <= RR; r++) v[r] = 0.0;
+          for (int j = tid; j < nblk; j += NB) {
+#pragma unroll
+            for (int r = 0; r <= RR; r++) v[r] += __ldcg(lml_part + (long long)j * (RMAX + 1) + (r == RR ? RMAX : r));
+          }
+#pragma unroll
+          for (int r = 0; r <= RR; r++) {
+            const double sv = warp_sum(v[r]);
+            if ((tid & 31) == 0) part[(tid >> 5) * (RR + 1) + r] = sv;
+          }
+        }
+        __syncthreads();
+        if (tid < R) {
+          const double qf = (part[0 * (RR + 1) + tid] + part[1 * (RR + 1) + tid]) + (part[2 * (RR + 1) + tid] + part[3 * (RR + 1) + tid]);
+          const double ld = (part[0 * (RR + 1) + RR] + part[1 * (RR + 1) + RR]) + (part[2 * (RR + 1) + RR] + part[3 * (RR + 1) + RR]);
+          lml_out[tid] = -0.5 * qf - ld - 0.5 * (double)N * 1.8378770664093454835606594728112;   // log(2 pi)
+        }
+      }
+      __syncthreads();          // part / sinv are rewritten by the next block of this CTA
+    }
   }
 }
 
@@ -323,8 +382,9 @@ extern "C" void gpm_debug_solve_ts(unsigned long long* out) { cudaMemcpyFromSymb
 #endif
 
 // first_dir = 1: alpha already holds z = L^{-1} Y (forward substitution fused into the factorisation): backward pass only
+// Y / lml (optional): the log marginal likelihood comes out of the backward pass itself (no pass of its own over L, Y, alpha)
 int solve_chain(gpm_handle_impl* h, const double* L, long long N, long long ldl, const double* invD,
-                double* alpha, int R, cudaStream_t stream, int first_dir) {
+                double* alpha, int R, cudaStream_t stream, int first_dir, const double* Y, double* lml) {
   const void* fns[2];
   if (R <= 1) { fns[0] = (const void*)solve_chain_kernel<false, 1>; fns[1] = (const void*)solve_chain_kernel<true, 1>; }
   else if (R <= 2) { fns[0] = (const void*)solve_chain_kernel<false, 2>; fns[1] = (const void*)solve_chain_kernel<true, 2>; }
@@ -337,12 +397,15 @@ int solve_chain(gpm_handle_impl* h, const double* L, long long N, long long ldl,
   int grid = nblk < h->sm_count ? nblk : h->sm_count;
   // flags are cleared on the stream before each direction (constant epoch), so the call sequence can be
   // captured into a CUDA graph and replayed
-  GPM_CUDA(cudaMemsetAsync(h->flags, 0, 2 * (size_t)h->n_flags * sizeof(int), stream));
+  GPM_CUDA(cudaMemsetAsync(h->flags, 0, 3 * (size_t)h->n_flags * sizeof(int), stream));
   for (int dir = first_dir; dir < 2; dir++) {
     int epoch = 1;
     int* flags = h->flags + dir * h->n_flags;
+    int* lml_flags = h->flags + 2 * h->n_flags;
+    double* lml_part = h->lml_part;
+    double* lml_out = dir == 1 ? lml : nullptr;
     void* args[] = {(void*)&L, (void*)&ldl, (void*)&N, (void*)&invD, (void*)&alpha, (void*)&R, (void*)&nblk,
-                    (void*)&flags, (void*)&epoch};
+                    (void*)&flags, (void*)&epoch, (void*)&Y, (void*)&lml_part, (void*)&lml_flags, (void*)&lml_out};
     GPM_CUDA(cudaLaunchCooperativeKernel(fns[dir], dim3(grid), dim3(CH_THREADS), args, CHAIN_SMEM, stream));
     count_launch(1);
   }
@@ -549,8 +612,8 @@ extern "C" int gpm_solve_lml(gpm_handle_t h, const double* L, int64_t N, int64_t
   gpm_handle_impl* hi = reinterpret_cast<gpm_handle_impl*>(h);
   int rc = hi->opt.solve_steps
                ? solve_blocked(L, N, ldl, reinterpret_cast<const double*>(potrf_ws), alpha, R, 1, 0, 0, 0, st)
-               : solve_chain(hi, L, N, ldl, reinterpret_cast<const double*>(potrf_ws), alpha, R, st, 0);
+               : solve_chain(hi, L, N, ldl, reinterpret_cast<const double*>(potrf_ws), alpha, R, st, 0, Y, lml);
   if (rc) return rc;
-  if (lml) return launch_lml(L, N, ldl, Y, alpha, R, lml, 1, 0, 0, st);
+  if (lml && hi->opt.solve_steps) return launch_lml(L, N, ldl, Y, alpha, R, lml, 1, 0, 0, st);
   return 0;
 }
