@@ -65,7 +65,7 @@ inline int make_theta(const double* theta, int D, Theta* out) {
 struct Options {
   int no_lookahead = 0;      // potrf: no look-ahead stream
   int tpc_wide = 4, tpc_narrow = 8;                    // potrf: tiles per CTA of the look-ahead updates
-  int wide_min = 32, wide4_min = 64, wide8_min = 96;   // potrf: outer panel width thresholds
+  int wide_min = 36, wide4_min = 64, wide8_min = 96;   // potrf: outer panel width thresholds (36: N = 4096, 32 block columns, is faster all-narrow: 2.00 vs 2.15 ms; N = 6144 keeps its wide start: 4.16 vs 4.30 ms; tools/potrf_sweep3.sh)
   int no_separable = 0;      // grid queries through the pointwise kernels
   int no_small_fused = 0;    // short paths through the tiled pipeline
   int no_small_tiles = 0;    // no latency tile kernel

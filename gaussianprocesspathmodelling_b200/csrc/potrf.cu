@@ -234,9 +234,9 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
 
   // Outer panels: wide panels make the trailing updates deep (K = 256 or 512: less C traffic and the tile
   // prologue/epilogue amortised over more slabs) but lengthen the serial panel chain, which must stay
-  // hidden behind the rest-update: width 8 while >= 96 block columns remain, 4 while >= 64, 2 while >= 32,
+  // hidden behind the rest-update: width 8 while >= 96 block columns remain, 4 while >= 64, 2 while >= 36,
   // then 1 (thresholds swept on B200 at N = 8192 and 16384, tools/potrf_sweep.sh and potrf_sweep2.sh; the response
-  // is flat within 1 % around these values).
+  // is flat within 1 % around these values; 36 rather than 32 keeps N = 4096 all-narrow, tools/potrf_sweep3.sh).
   // Large batches are throughput-bound in every launch, so they use width 2 and no look-ahead.
   const int wide_env = h->opt.wide_min, wide4_env = h->opt.wide4_min, wide8_env = h->opt.wide8_min;
   std::vector<int> pb(nblk + 1), pw(nblk + 1);
