@@ -227,11 +227,24 @@ def cpu_cfg3_sample(n_serial=48, n_pool_per_core=12):
                                       "the pool runs one single-threaded fit per core"}
 
 
+def cpu_kmeans_sample(P=1500, k=8, n=33):
+    """One Lloyd iteration of the reference's k-means (the oracle's restatement of GPmap.py:65-121, Python loops over
+    paths and centroids with numpy inside calc_distance, as the reference runs it) on a bounded sample of paths."""
+    from oracle import gp_ref
+    from gaussianprocesspathmodelling_b200 import workloads as wl
+    xs, ys, ts = wl.trajectory_families(P, k, n, seed=5)
+    t0 = time.perf_counter()
+    gp_ref.lloyd(xs, ys, ts, list(range(k)), threshold=0.0, max_iter=1)
+    dt = time.perf_counter() - t0
+    return {"sample_paths": P, "clusters": k, "s_per_iteration_on_sample": dt, "path_assignments_per_s": P / dt,
+            "note": "single-threaded by construction (a Python double loop, GPmap.py:72-80)"}
+
+
 def run_cpu_sample(args):
     """`--cpu-sample`: print the CPU baseline as one JSON object (run by the B200 arm in a clean subprocess)."""
     cpu_sample(1024)                                            # warm-up (imports, BLAS thread pools)
     v, det = cpu_sample(args.cpu_points)
-    out = {"value": v, "detail": det, "cfg3": cpu_cfg3_sample()}
+    out = {"value": v, "detail": det, "cfg3": cpu_cfg3_sample(), "kmeans": cpu_kmeans_sample()}
     print(json.dumps(out))
 
 
@@ -632,6 +645,27 @@ def run_b200(args):
         extra["short_paths_N33"] = {"paths_per_gpu": Bs, "N": 33, "ms": t_s, "fits_per_s": world * Bs / (t_s * 1e-3),
                                     "kernel": "fit_small_kernel: one CTA per path, whole fit in shared memory"}
         del Xsd, Ysd
+        # the reference's real hot loop, trajectories.kmeansclustering (GPmap.py:36-121), device-resident: time per Lloyd
+        # iteration (assignment + member-order centroid means + convergence sum) on 100000 synthetic 33-point trajectories
+        Pk, kk, nk = 100000, 8, 33
+        kx, ky, kt = wl.trajectory_families(Pk, kk, nk, seed=5 + rank)
+        kdev = torch.from_numpy(np.stack([kx, ky, kt])).to(dev)
+        kxT, kyT = kdev[0].t().contiguous(), kdev[1].t().contiguous()
+        ksel = torch.arange(kk, device=dev)
+        kws = torch.empty(int(lib.gpm_kmeans_workspace_bytes(Pk, nk, kk)) // 8, dtype=torch.float64, device=dev)
+        kassign = torch.zeros(Pk, dtype=torch.int32, device=dev)
+
+        def k_lloyd(iters=10):
+            cents = kdev[:, ksel, :].contiguous()
+            # threshold 0: never converges early, every enqueued iteration does its full work
+            _native.check(lib.gpm_kmeans_lloyd(h, ptr(kdev[0]), ptr(kdev[1]), ptr(kdev[2]), ptr(kxT), ptr(kyT), Pk, nk, kk,
+                                               ptr(cents), ptr(kassign), 0.0, iters, 1, ptr(kws), st), "kmeans_lloyd")
+        t_k = max_over_ranks(timed(torch, k_lloyd, 3, warm=1)) / 10
+        extra["kmeans_lloyd"] = {"paths_per_gpu": Pk, "samples_per_path": nk, "clusters": kk, "ms_per_iteration": t_k,
+                                 "path_assignments_per_s": world * Pk / (t_k * 1e-3),
+                                 "note": "assignment (calc_distance, GPmap.py:114-121) + centroid means in member order "
+                                         "(calc_mean_traj, bit-exact with the reference) + convergence sum, all on the device"}
+        del kdev, kxT, kyT, kws
         GPmap.clear_workspaces()
         torch.cuda.empty_cache()
         # -- config 5, STRONG scaling: fixed 2048x2048 grid on the N=16384 model, grid points sharded over the ranks,
@@ -708,7 +742,7 @@ def run_b200(args):
                    "sample": f"numpy/scipy oracle: full N=4096 fit ({det['fit_s']:.2f}s) + posterior on 16384 of 262144 grid points "
                              f"({det['predict_sample_s']:.2f}s), extrapolated linearly to the whole grid",
                    "host_cores": det["host_cores"], "per_step_s_full_grid": det["per_step_s_full_grid"],
-                   "cfg3_N512_fits": res["cfg3"]}
+                   "cfg3_N512_fits": res["cfg3"], "kmeans_lloyd": res.get("kmeans")}
 
     if rank == 0:
         line = {

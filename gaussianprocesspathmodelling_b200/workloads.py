@@ -92,3 +92,17 @@ CONFIGS = {
     "cfg4": dict(N=16384, D=2, seed=4),
     "cfg5": dict(N=16384, D=2, G=2048, seed=5),
 }
+
+
+def trajectory_families(P, k, n=33, seed=5, jitter=800.0):
+    """P synthetic fixed-length 2-D trajectories in k families (a random straight segment per family in the reference's
+    +-5e4 box, per-sample Gaussian jitter): xs, ys, ts of shape (P, n) -- the input of trajectories.kmeansclustering
+    (GPmap.py:36-121), which resamples every trajectory to 33 points (GPmap.py:189)."""
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(-4.0e4, 4.0e4, (k, 2)); b = rng.uniform(-4.0e4, 4.0e4, (k, 2))
+    fam = rng.integers(0, k, P)
+    t = np.linspace(0.0, 1.0, n)
+    xs = a[fam, 0:1] + (b[fam, 0:1] - a[fam, 0:1]) * t + rng.normal(0.0, jitter, (P, n))
+    ys = a[fam, 1:2] + (b[fam, 1:2] - a[fam, 1:2]) * t + rng.normal(0.0, jitter, (P, n))
+    ts = np.tile(np.arange(n, dtype=np.float64), (P, 1))
+    return xs, ys, ts

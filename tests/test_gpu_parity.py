@@ -313,6 +313,21 @@ def test_c_abi_argument_errors():
     assert b"argument 7" in lib.gpm_last_error()
     bad = _native.theta_array([1.0, -1.0, 1.0, 0.1])
     assert lib.gpm_cov(h, C.c_void_p(x.data_ptr()), 8, 2, bad, C.c_void_p(k.data_ptr()), 8, 0, st) == -5
+    # gpm_fit: the one-call fit validates every argument before it launches anything
+    p = lambda t: C.c_void_p(t.data_ptr())
+    y = torch.zeros(8, 2, dtype=torch.float64, device="cuda"); a = torch.zeros_like(y)
+    ws = torch.zeros(int(lib.gpm_potrf_workspace_bytes(8)) // 8, dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda"); lml = torch.zeros(2, dtype=torch.float64, device="cuda")
+    fit = lambda *v: lib.gpm_fit(*v)
+    assert fit(None, p(x), 8, 2, th, p(y), 2, p(k), 8, p(ws), p(a), p(lml), p(info), st) == -1
+    assert fit(h, p(x), 0, 2, th, p(y), 2, p(k), 8, p(ws), p(a), p(lml), p(info), st) == -3
+    assert fit(h, p(x), 8, 2, bad, p(y), 2, p(k), 8, p(ws), p(a), p(lml), p(info), st) == -5
+    assert fit(h, p(x), 8, 2, th, p(y), 9, p(k), 8, p(ws), p(a), p(lml), p(info), st) == -7
+    assert fit(h, p(x), 8, 2, th, p(y), 2, p(k), 7, p(ws), p(a), p(lml), p(info), st) == -9
+    assert fit(h, p(x), 8, 2, th, p(y), 2, p(k), 8, p(ws), p(y), p(lml), p(info), st) == -11      # alpha must not alias Y
+    assert fit(h, p(x), 8, 2, th, p(y), 2, p(k), 8, p(ws), p(a), p(lml), None, st) == -13
+    assert fit(h, p(x), 8, 2, th, p(y), 2, p(k), 8, p(ws), p(a), None, p(info), st) == 0           # lml is optional
+    torch.cuda.synchronize()
 
 
 def test_cross_cov_materialised_matches_oracle():
