@@ -53,112 +53,180 @@ kmeans_assign_kernel(const double* __restrict__ pxT, const double* __restrict__ 
   assign[p] = best_c;
 }
 
-// One CTA per centroid; thread (a, i) owns sample i of array a in {xs, ys, timestamp}.  px, py, pt: [P][n].
-// cold / cnew: [3][k][n] (xs, ys, timestamp planes).  An empty cluster keeps its previous centroid.
-//
-// The additions of a centroid's members are a serial chain by construction (path order, the order the reference
-// appends them to the cluster list: calc_mean_traj is bit-exact that way); the LOADS need not be.  Paths are scanned in
-// chunks of 2048: the eight warps compact the chunk's members with ballots into one ordered list, the members' rows are
-// then gathered into shared memory by all threads (a warp per row) with asynchronous 8-byte copies (stage_rows rows per stage, two
-// stages: the gather of group g + 1 flies while group g is summed), and the 3n summing threads add the staged rows in
-// order.  The first version loaded each member's value right before its addition: one DRAM round trip per member
-// (ncu: 13 GB/s, issue slots 2 % busy), 5.1 ms per Lloyd iteration at P = 100000, k = 8; this one 1.1 ms (assignment
-// 0.085 ms of it).  What is left is the gather itself on k SMs; gathering with all SMs into an ordered per-centroid
-// buffer first (a global order-preserving compaction) is the next step.
-constexpr int KM_CH = 2048;
+// ------------------------------------------------------------------------------------------------------------------
+// Centroid update (calc_mean_traj, GPmap.py:95-112).  The additions of a centroid's members are a serial chain by
+// construction -- path order, the order the reference appends them to the cluster list: the mean is bit-exact that way
+// -- but finding the members and fetching their rows need not be serial, nor run on k SMs only:
+//   rank    (all SMs)   every path gets its rank among the paths of its 2048-path chunk that share its centroid
+//                       (__match_any_sync inside a warp, per-warp tables across the warps of a round); per-chunk counts
+//   scan    (one CTA)   exclusive scan of the counts over the chunks, per centroid; row offset of every centroid's region
+//   gather  (all SMs)   row p of (xs, ys, timestamp) -> row offset[c] + chunk_offset + rank of ONE ordered buffer
+//   sum     (k CTAs)    a centroid streams its contiguous region through shared memory (16-byte asynchronous copies,
+//                       two stages) and its 3n summing threads add the rows in order
+// History (P = 100000, n = 33, k = 8, per Lloyd iteration): each member's value loaded right before its addition
+// 5.1 ms (ncu: 13 GB/s, issue slots 2 %: one DRAM round trip per member); in-kernel ballot compaction + staged gather on
+// k SMs 1.1 ms; this version 0.56 ms = assignment 0.083 + rank 0.011 + scan 0.004 + gather 0.03 + sum 0.43.  The sum
+// streams 10 MB per centroid through ONE SM at about 30 GB/s (stage sizes of 64 and 128 rows give 2.7 and 4.4 us per
+// stage: 1 us of latency + bytes / 30 GB/s); a chain of several CTAs per centroid, each staging its segment of the
+// region and passing the running sums on, would spread that over more SMs without changing the order of the additions.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int KM_CH = 2048;              // paths per chunk (one CTA of the rank / gather kernels)
+constexpr int KM_THREADS = 256, KM_WARPS = KM_THREADS / 32;
+constexpr int KM_ROUNDS = KM_CH / KM_THREADS;
 
-__device__ __forceinline__ void km_cp_async8(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void km_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-constexpr int KM_THREADS = 256, KM_WARPS = KM_THREADS / 32;    // all warps gather, the first 3n threads also sum (1024 threads measured no faster)
+// lrank[p] = number of paths q < p of p's chunk with assign[q] == assign[p];  counts[chunk][c] = members of c in the chunk
+__global__ void __launch_bounds__(KM_THREADS)
+kmeans_rank_kernel(const int* __restrict__ assign, long long P, int k, int* __restrict__ lrank,
+                   int* __restrict__ counts, const KmState* __restrict__ state) {
+  if (state->converged) return;
+  extern __shared__ int km_tab[];          // cnt[k] running counts of the chunk, then wtab[KM_WARPS][k] of the round
+  int* cnt = km_tab;
+  int* wtab = km_tab + k;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long p0 = (long long)blockIdx.x * KM_CH;
+  for (int e = tid; e < k; e += KM_THREADS) cnt[e] = 0;
+  for (int r = 0; r < KM_ROUNDS; r++) {
+    const long long p = p0 + r * KM_THREADS + tid;
+    const int a = p < P ? assign[p] : -1;
+    for (int e = tid; e < KM_WARPS * k; e += KM_THREADS) wtab[e] = 0;
+    __syncthreads();
+    const unsigned same = __match_any_sync(0xffffffffu, a);
+    const int before = __popc(same & ((1u << lane) - 1u));
+    if (a >= 0 && before == 0) wtab[warp * k + a] = __popc(same);      // the group's first lane
+    __syncthreads();
+    if (a >= 0) {
+      int base = cnt[a];
+      for (int w = 0; w < warp; w++) base += wtab[w * k + a];
+      lrank[p] = base + before;
+    }
+    __syncthreads();
+    for (int e = tid; e < k; e += KM_THREADS) {
+      int t = cnt[e];
+#pragma unroll
+      for (int w = 0; w < KM_WARPS; w++) t += wtab[w * k + e];
+      cnt[e] = t;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < k; e += KM_THREADS) counts[(long long)blockIdx.x * k + e] = cnt[e];
+}
 
+// choff[chunk][c] = members of c in earlier chunks; total[c]; coff[c] = first row of c's region (even: 16-byte aligned rows)
+__global__ void __launch_bounds__(1024)
+kmeans_scan_kernel(const int* __restrict__ counts, int nchunks, int k, int* __restrict__ choff,
+                   long long* __restrict__ total, long long* __restrict__ coff, const KmState* __restrict__ state) {
+  if (state->converged) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < k; c += 32) {
+    long long run = 0;
+    for (int t0 = 0; t0 < nchunks; t0 += 32) {
+      const int ch = t0 + lane;
+      const int v = ch < nchunks ? counts[(long long)ch * k + c] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+      if (ch < nchunks) choff[(long long)ch * k + c] = (int)(run + inc - v);
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) total[c] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long r = 0;
+    for (int c = 0; c < k; c++) { coff[c] = r; r += (total[c] + 1) & ~1ll; }
+  }
+}
+
+// row p of xs / ys / timestamp -> row coff[c] + choff[chunk][c] + lrank[p] of the ordered buffer G ([rows][3n])
+__global__ void __launch_bounds__(KM_THREADS)
+kmeans_gather_kernel(const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pt,
+                     long long P, int n, int k, const int* __restrict__ assign, const int* __restrict__ lrank,
+                     const int* __restrict__ choff, const long long* __restrict__ coff, double* __restrict__ G,
+                     const KmState* __restrict__ state) {
+  if (state->converged) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * KM_WARPS + warp;       // a warp per path: every copy of the launch is independent
+  if (p >= P) return;
+  const int c = assign[p];
+  const long long row = coff[c] + choff[(p / KM_CH) * k + c] + lrank[p];
+  double* dst = G + row * 3 * n;
+  const long long src = p * n;
+  for (int i = lane; i < n; i += 32) {
+    dst[i] = px[src + i];
+    dst[n + i] = py[src + i];
+    dst[2 * n + i] = pt[src + i];
+  }
+}
+
+// One CTA per centroid; thread w < 3n owns entry w of a row (xs | ys | timestamp).  cold / cnew: [3][k][n].
+// An empty cluster keeps its previous centroid.
 __global__ void __launch_bounds__(KM_THREADS, 1)
-kmeans_update_kernel(const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pt,
-                     long long P, int n, int k, const int* __restrict__ assign, const double* __restrict__ cold,
-                     double* __restrict__ cnew, double* __restrict__ shift_c, const KmState* __restrict__ state,
-                     int stage_rows) {
+kmeans_update_kernel(const double* __restrict__ G, int n, int k, const long long* __restrict__ total,
+                     const long long* __restrict__ coff, const double* __restrict__ cold, double* __restrict__ cnew,
+                     double* __restrict__ shift_c, const KmState* __restrict__ state, int stage_rows) {
   if (state->converged) return;
   extern __shared__ __align__(16) double km_stage[];      // [2][stage_rows][3n]
-  constexpr int WCH = KM_CH / KM_WARPS;
-  __shared__ int members[KM_CH];
-  __shared__ int wcnt[KM_WARPS];
-  __shared__ long long total;
-  const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = blockIdx.x, tid = threadIdx.x;
   const int work = 3 * n;
-  if (tid == 0) total = 0;
-  // each thread carries up to SLOTS running sums (sample slots tid, tid + KM_THREADS, ...)
-  constexpr int SLOTS = 2048 / KM_THREADS; // 3 n <= 2048
+  const long long m = total[c];
+  const double* region = G + coff[c] * work;               // 16-byte aligned: coff is even and so is stage_rows
+  // each thread carries up to SLOTS running sums (entries tid, tid + KM_THREADS, ...)
+  constexpr int SLOTS = 2048 / KM_THREADS;                 // 3 n <= 2048
   double sum[SLOTS];
 #pragma unroll
   for (int s = 0; s < SLOTS; s++) sum[s] = 0.0;
-  for (long long p0 = 0; p0 < P; p0 += KM_CH) {
-    unsigned masks[WCH / 32];
-    int mw = 0;
-    const long long base = p0 + (long long)warp * WCH;
-#pragma unroll
-    for (int r = 0; r < WCH / 32; r++) {
-      const long long pp = base + r * 32 + lane;
-      masks[r] = __ballot_sync(0xffffffffu, pp < P && assign[pp] == c);
-      mw += __popc(masks[r]);
-    }
-    __syncthreads();                       // the previous chunk's list and stages have been consumed
-    if (lane == 0) wcnt[warp] = mw;
-    __syncthreads();
-    int off = 0, m = 0;
-#pragma unroll
-    for (int w = 0; w < KM_WARPS; w++) { if (w < warp) off += wcnt[w]; m += wcnt[w]; }
-#pragma unroll
-    for (int r = 0; r < WCH / 32; r++) {
-      if (masks[r] & (1u << lane)) members[off + __popc(masks[r] & ((1u << lane) - 1u))] = warp * WCH + r * 32 + lane;
-      off += __popc(masks[r]);
-    }
-    __syncthreads();
-    if (tid == 0) total += m;
-    // gather rows [g0, g0 + cnt) of the member list into stage `buf` (asynchronous copies, one commit group)
-    auto gather = [&](int buf, int g0, int cnt) {
-      const uint32_t dst0 = smem_u32(km_stage + (size_t)buf * stage_rows * work);
-      for (int row = warp; row < cnt; row += KM_WARPS) {   // a warp per member row: no index divisions in the loop
-        const long long roff = (p0 + members[g0 + row]) * (long long)n;
-        const uint32_t d = dst0 + (uint32_t)(row * work) * 8u;
-        for (int i = lane; i < n; i += 32) {
-          km_cp_async8(d + (uint32_t)i * 8u, px + roff + i);
-          km_cp_async8(d + (uint32_t)(n + i) * 8u, py + roff + i);
-          km_cp_async8(d + (uint32_t)(2 * n + i) * 8u, pt + roff + i);
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    const int ngroups = (m + stage_rows - 1) / stage_rows;
-    if (ngroups > 0) gather(0, 0, min(stage_rows, m));
-    for (int g = 0; g < ngroups; g++) {
-      if (g + 1 < ngroups) {
-        gather((g + 1) & 1, (g + 1) * stage_rows, min(stage_rows, m - (g + 1) * stage_rows));
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
-      __syncthreads();                     // every thread's copies of group g have landed
-      const int cnt = min(stage_rows, m - g * stage_rows);
-      const double* sb = km_stage + (size_t)(g & 1) * stage_rows * work;
-#pragma unroll 1
-      for (int s = 0; s < SLOTS; s++) {
-        const int w = tid + KM_THREADS * s;
-        if (w >= work) break;
-        double acc = 0.0;
-#pragma unroll
-        for (int t = 0; t < SLOTS; t++) if (t == s) acc = sum[t];
-        const double* col = sb + w;
-#pragma unroll 8
-        for (int r = 0; r < cnt; r++) acc = __dadd_rn(acc, col[(size_t)r * work]);
-#pragma unroll
-        for (int t = 0; t < SLOTS; t++) if (t == s) sum[t] = acc;
-      }
-      __syncthreads();                     // stage g & 1 may be refilled (by the gather of group g + 2)
-    }
-  }
+  // rows [g0, g0 + cnt) of the region into stage `buf`: contiguous, so ONE thread moves them with bulk asynchronous
+  // copies (TMA, completion counted in bytes on the stage's mbarrier).  Plain or cp.async loads top out near 20 GB/s
+  // for a single SM (ncu on the previous version: 164 GB/s over the 8 busy SMs); an odd row count is rounded up to
+  // 16 bytes and reads eight bytes into the next row, which exists: the buffer is padded.
+  __shared__ __align__(8) unsigned long long km_bar[2];
+  const uint32_t bar0 = smem_u32(&km_bar[0]);
+  if (tid == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); fence_mbar_init(); }
   __syncthreads();
-  const long long cnt = total;
+  auto gather = [&](int buf, long long g0, int cnt) {       // thread 0 only
+    const uint32_t dst0 = smem_u32(km_stage + (size_t)buf * stage_rows * work), bar = bar0 + 8u * buf;
+    const char* src = reinterpret_cast<const char*>(region + g0 * work);
+    const uint32_t bytes = ((uint32_t)(cnt * work) * 8u + 15u) & ~15u;
+    mbar_arrive_expect_tx(bar, bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768u) {
+      const uint32_t sz = bytes - o < 32768u ? bytes - o : 32768u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst0 + o), "l"(src + o), "r"(sz), "r"(bar) : "memory");
+    }
+  };
+  uint32_t par = 0;                                          // bit b: parity of stage b's next completed phase
+  const long long ngroups = (m + stage_rows - 1) / stage_rows;
+  if (ngroups > 0 && tid == 0) gather(0, 0, (int)(m < stage_rows ? m : stage_rows));
+  for (long long g = 0; g < ngroups; g++) {
+    if (g + 1 < ngroups && tid == 0) {                       // stage (g + 1) & 1 was released by the barrier that ended group g - 1
+      const long long left = m - (g + 1) * stage_rows;
+      gather((int)((g + 1) & 1), (g + 1) * stage_rows, (int)(left < stage_rows ? left : stage_rows));
+    }
+    mbar_wait(bar0 + 8u * (uint32_t)(g & 1), (par >> (g & 1)) & 1u);
+    par ^= 1u << (g & 1);
+    const long long left = m - g * stage_rows;
+    const int cnt = (int)(left < stage_rows ? left : stage_rows);
+    const double* sb = km_stage + (size_t)(g & 1) * stage_rows * work;
+#pragma unroll 1
+    for (int s = 0; s < SLOTS; s++) {
+      const int w = tid + KM_THREADS * s;
+      if (w >= work) break;
+      double acc = 0.0;
+#pragma unroll
+      for (int t = 0; t < SLOTS; t++) if (t == s) acc = sum[t];
+      const double* col = sb + w;
+#pragma unroll 8
+      for (int r = 0; r < cnt; r++) acc = __dadd_rn(acc, col[(size_t)r * work]);
+#pragma unroll
+      for (int t = 0; t < SLOTS; t++) if (t == s) sum[t] = acc;
+    }
+    __syncthreads();                       // stage g & 1 may be refilled (by the gather of group g + 2)
+  }
+  const long long cnt = m;
 #pragma unroll
   for (int s = 0; s < SLOTS; s++) {
     const int w = tid + KM_THREADS * s;
@@ -213,10 +281,33 @@ extern "C" int gpm_kmeans_assign(gpm_handle_t h, const double* pxT, const double
   return 0;
 }
 
+// workspace layout: second centroid buffer [3][k][n] | per-centroid shifts [k] | state (2 doubles) |
+//   total [k], coff [k] (int64) | lrank [P], counts [nchunks][k], choff [nchunks][k] (int32, padded to 16 bytes) |
+//   ordered row buffer G [(P + 2k + 2)][3n]
+struct KmLayout {
+  size_t shift_off, state_off, total_off, coff_off, lrank_off, counts_off, choff_off, g_off, bytes;
+  long long nchunks;
+};
+static KmLayout km_layout(long long P, int n, int k) {
+  KmLayout L;
+  L.nchunks = (P + KM_CH - 1) / KM_CH;
+  size_t o = (size_t)3 * k * n * 8;
+  L.shift_off = o; o += (size_t)k * 8;
+  L.state_off = o; o += 16;
+  L.total_off = o; o += (size_t)k * 8;
+  L.coff_off = o; o += (size_t)k * 8;
+  L.lrank_off = o; o += (size_t)P * 4;
+  L.counts_off = o; o += (size_t)L.nchunks * k * 4;
+  L.choff_off = o; o += (size_t)L.nchunks * k * 4;
+  o = (o + 15) & ~(size_t)15;
+  L.g_off = o; o += (size_t)(P + 2 * (long long)k + 2) * 3 * n * 8;
+  L.bytes = o;
+  return L;
+}
+
 extern "C" size_t gpm_kmeans_workspace_bytes(int64_t P, int32_t n, int32_t k) {
   if (P <= 0 || n <= 0 || k <= 0) return 0;
-  // second centroid buffer [3][k][n] + per-centroid shifts [k] + state
-  return ((size_t)3 * k * n + (size_t)k + 2) * sizeof(double);
+  return km_layout(P, n, k).bytes;
 }
 
 extern "C" int gpm_kmeans_lloyd(gpm_handle_t h, const double* px, const double* py, const double* pt,
@@ -228,25 +319,38 @@ extern "C" int gpm_kmeans_lloyd(gpm_handle_t h, const double* px, const double* 
   GPM_ARG(pxT != nullptr && pyT != nullptr, 5);
   GPM_ARG(P > 0, 7);
   GPM_ARG(n > 0 && 3 * n <= 2048, 8);
-  GPM_ARG(k > 0 && (size_t)k * n * 16 <= 200 * 1024, 9);
+  GPM_ARG(k > 0 && (size_t)k * n * 16 <= 200 * 1024 && k <= 4096, 9);
   GPM_ARG(centroids != nullptr, 10);
   GPM_ARG(assign != nullptr, 11);
   GPM_ARG(iters >= 0, 13);
-  GPM_ARG(ws != nullptr && ((uintptr_t)ws & 7) == 0, 15);
+  GPM_ARG(ws != nullptr && ((uintptr_t)ws & 15) == 0, 15);
   DeviceGuard guard(reinterpret_cast<gpm_handle_impl*>(h)->device);
   cudaStream_t st = (cudaStream_t)stream;
-  double* buf1 = reinterpret_cast<double*>(ws);
-  double* shift_c = buf1 + (size_t)3 * k * n;
-  KmState* state = reinterpret_cast<KmState*>(shift_c + k);
+  const KmLayout L = km_layout(P, n, k);
+  char* wsb = reinterpret_cast<char*>(ws);
+  double* buf1 = reinterpret_cast<double*>(wsb);
+  double* shift_c = reinterpret_cast<double*>(wsb + L.shift_off);
+  KmState* state = reinterpret_cast<KmState*>(wsb + L.state_off);
+  long long* total = reinterpret_cast<long long*>(wsb + L.total_off);
+  long long* coff = reinterpret_cast<long long*>(wsb + L.coff_off);
+  int* lrank = reinterpret_cast<int*>(wsb + L.lrank_off);
+  int* counts = reinterpret_cast<int*>(wsb + L.counts_off);
+  int* choff = reinterpret_cast<int*>(wsb + L.choff_off);
+  double* G = reinterpret_cast<double*>(wsb + L.g_off);
   if (first) GPM_CUDA(cudaMemsetAsync(state, 0, sizeof(KmState), st));
   const size_t smem = (size_t)k * n * 16;
   if (smem > 48 * 1024)
     GPM_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t plane = (size_t)k * n;
-  // staged member rows of the centroid update: two stages of up to 128 rows of 3n doubles, within 200 KB
-  const int stage_rows = (int)std::max<size_t>(1, std::min<size_t>(128, (100 * 1024) / ((size_t)3 * n * 8)));
-  const size_t upd_smem = (size_t)2 * stage_rows * 3 * n * sizeof(double);
+  // staged rows of the centroid sum: two stages of up to 128 rows (an even number) of 3n doubles, within 200 KB
+  int stage_rows = (int)std::max<size_t>(2, std::min<size_t>(128, (100 * 1024) / ((size_t)3 * n * 8)));
+  stage_rows &= ~1;
+  const size_t upd_smem = (size_t)2 * stage_rows * 3 * n * sizeof(double) + 16;
   GPM_CUDA(cudaFuncSetAttribute(kmeans_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+  const size_t rank_smem = (size_t)(KM_WARPS + 1) * k * sizeof(int);
+  if (rank_smem > 48 * 1024)
+    GPM_CUDA(cudaFuncSetAttribute(kmeans_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
+  const unsigned nchunks = (unsigned)L.nchunks;
   // Iterations ping-pong between `centroids` (even) and the workspace buffer (odd).  Once `converged` is set every
   // later kernel is a no-op, so state->iters tells the caller which buffer holds the final centroids; an even
   // number of enqueued iterations per call keeps the parity bookkeeping on the caller's side trivial.
@@ -256,7 +360,13 @@ extern "C" int gpm_kmeans_lloyd(gpm_handle_t h, const double* px, const double* 
     double* nxt = (it & 1) ? centroids : buf1;
     kmeans_assign_kernel<<<(unsigned)((P + 127) / 128), 128, smem, st>>>(pxT, pyT, P, n, cur, cur + plane, k, nullptr, assign, state);
     GPM_LAUNCH_CHECK();
-    kmeans_update_kernel<<<k, KM_THREADS, upd_smem, st>>>(px, py, pt, P, n, k, assign, cur, nxt, shift_c, state, stage_rows);
+    kmeans_rank_kernel<<<nchunks, KM_THREADS, rank_smem, st>>>(assign, P, k, lrank, counts, state);
+    GPM_LAUNCH_CHECK();
+    kmeans_scan_kernel<<<1, 1024, 0, st>>>(counts, (int)nchunks, k, choff, total, coff, state);
+    GPM_LAUNCH_CHECK();
+    kmeans_gather_kernel<<<(unsigned)((P + KM_WARPS - 1) / KM_WARPS), KM_THREADS, 0, st>>>(px, py, pt, P, n, k, assign, lrank, choff, coff, G, state);
+    GPM_LAUNCH_CHECK();
+    kmeans_update_kernel<<<k, KM_THREADS, upd_smem, st>>>(G, n, k, total, coff, cur, nxt, shift_c, state, stage_rows);
     GPM_LAUNCH_CHECK();
     kmeans_finish_kernel<<<1, 32, 0, st>>>(shift_c, k, threshold, state);
     GPM_LAUNCH_CHECK();
@@ -270,8 +380,8 @@ extern "C" int gpm_kmeans_state(gpm_handle_t h, const void* ws, int32_t n, int32
   GPM_ARG(ws != nullptr, 2);
   GPM_ARG(n > 0 && k > 0, 3);
   DeviceGuard guard(reinterpret_cast<gpm_handle_impl*>(h)->device);
-  const double* buf1 = reinterpret_cast<const double*>(ws);
-  const KmState* state = reinterpret_cast<const KmState*>(buf1 + (size_t)3 * k * n + k);
+  // the state sits right behind the second centroid buffer and the shifts, whatever P is
+  const KmState* state = reinterpret_cast<const KmState*>(reinterpret_cast<const char*>(ws) + ((size_t)3 * k * n + k) * 8);
   KmState hs;
   GPM_CUDA(cudaMemcpyAsync(&hs, state, sizeof(KmState), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   GPM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));

@@ -36,7 +36,9 @@ def test_workspace_queries_need_no_gpu():
     assert lib.gpm_potrf_workspace_bytes(4096) == 32 * 128 * 128 * 8
     assert lib.gpm_potrf_workspace_bytes(200) == 2 * 128 * 128 * 8
     assert lib.gpm_fit_batched_workspace_bytes(None, 3, 512) == 0      # depends on the handle's options: needs a handle
-    assert lib.gpm_kmeans_workspace_bytes(100, 33, 3) == (3 * 3 * 33 + 3 + 2) * 8
+    # second centroid buffer + shifts + state, the rank / count tables and the ordered row buffer (P + 2k + 2 rows of 3n)
+    assert lib.gpm_kmeans_workspace_bytes(100, 33, 3) >= (3 * 3 * 33 + 3 + 2) * 8 + (100 + 2 * 3 + 2) * 3 * 33 * 8
+    assert lib.gpm_kmeans_workspace_bytes(100, 33, 3) % 16 == 0
     assert lib.gpm_potrf_workspace_bytes(0) == 0
 
 
