@@ -15,7 +15,11 @@
 // the solve through shared memory, and what a path writes (its sub-diagonal L tiles and the inverted diagonal
 // blocks, 1.3 MB in a per-CTA scratch that is reused for every path of the CTA) is read back while it is still in L2.
 // The latency-bound diagonal factorisations of one path overlap the tensor-core phases of the other path on the
-// same SM: that is what the hardware's warp schedulers do with two resident CTAs, no software pipelining needed.
+// same SM -- in part: DMMA and DFMA share one pipe per scheduler, so the serial FP64 chains of one CTA queue behind the
+// other CTA's tile loops (measured: two co-resident paths take 898 us each against 725 us alone).  ncu
+// counts 5.0 MB of HBM traffic per path (the 296 scratches do not all stay in L2) against the tiled pipeline's 9.2 MB.
+// gpm_fit_batched takes this kernel for batches of at most one wave of CTAs (and when the tiled workspace would pass
+// 32 GB); larger batches measure 2 - 6 % faster through the tiled pipeline (batched.cu: use_path_fit).
 //
 // CTA = 4 warps (tile = 64 rows x 128 columns, warp tile 64 x 32 as 8 x 4 DMMA sub-tiles, 128 accumulator registers
 // per thread).  There is no producer warp: ten warps per SM would put three on one scheduler and cap the kernel at
