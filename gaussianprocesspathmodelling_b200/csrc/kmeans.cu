@@ -66,9 +66,13 @@ kmeans_assign_kernel(const double* __restrict__ pxT, const double* __restrict__ 
 // History (P = 100000, n = 33, k = 8, per Lloyd iteration): each member's value loaded right before its addition
 // 5.1 ms (ncu: 13 GB/s, issue slots 2 %: one DRAM round trip per member); in-kernel ballot compaction + staged gather on
 // k SMs 1.1 ms; this version 0.56 ms = assignment 0.083 + rank 0.011 + scan 0.004 + gather 0.03 + sum 0.43.  The sum
-// streams 10 MB per centroid through ONE SM at about 30 GB/s (stage sizes of 64 and 128 rows give 2.7 and 4.4 us per
-// stage: 1 us of latency + bytes / 30 GB/s); a chain of several CTAs per centroid, each staging its segment of the
-// region and passing the running sums on, would spread that over more SMs without changing the order of the additions.
+// streams 10 MB per centroid from DRAM through ONE SM at about 30 GB/s (stage sizes of 64 and 128 rows give 2.7 and
+// 4.4 us per stage: 1 us of latency + bytes / 30 GB/s).  Measured on top and not kept, all at 0.55 - 0.65 ms: four
+// stages of 64 rows (three bulk copies in flight), bulk copies in 4 KB pieces (slower) or one per stage, sixteen loads
+// ahead of their additions in the inner loop, evict-first loads in the gather so that the ordered buffer stays in L2,
+// and a chain of 16 CTAs per centroid passing the running sums on (each CTA can prefetch only its two stages, so the
+// later stages of its segment still load on the chain).  A chain in which every CTA owns every 16th two-stage segment,
+// with the next one prefetched while the chain is elsewhere, is what would spread the stream over more SMs.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int KM_CH = 2048;              // paths per chunk (one CTA of the rank / gather kernels)
 constexpr int KM_THREADS = 256, KM_WARPS = KM_THREADS / 32;
