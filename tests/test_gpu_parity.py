@@ -789,3 +789,22 @@ def test_fit_with_fused_forward_substitution_equals_the_three_step_path(N, R):
     # deterministic: the same call again is bitwise the same
     m2 = GPmap.fit_gp(X, Y, theta=th)
     assert torch.equal(m1.alpha, m2.alpha) and torch.equal(m1.lml_dev, m2.lml_dev)
+
+
+def test_fit_under_a_concurrent_sm_hogging_stream_is_bitwise_the_quiet_result():
+    """The in-place panel solves (strip kernel: a CTA reads only the rows it writes) must not depend on how the block
+    scheduler staggers their CTAs: the same fit while another stream keeps every SM busy with large GEMMs -- so that
+    the fit's CTAs are admitted one by one as SMs free up -- must reproduce the quiet result bit for bit.  (Round 1's
+    quarter-split kernel had an inter-CTA read-after-write race here that idle-GPU tests could not see.)"""
+    X, Y, th = wl.single_path(2500, seed=77, D=2, R=2)
+    m0 = GPmap.fit_gp(X, Y, theta=th)
+    L0, a0, l0 = m0.L.clone(), m0.alpha.clone(), m0.lml_dev.clone()
+    side = torch.cuda.Stream()
+    A = torch.randn(8192, 8192, device="cuda")
+    for trial in range(3):
+        with torch.cuda.stream(side):
+            for _ in range(4 + 2 * trial):
+                B = A @ A                                    # noqa: F841  (tens of ms of SM-filling work)
+        m1 = GPmap.fit_gp(X, Y, theta=th)
+        torch.cuda.synchronize()
+        assert torch.equal(m1.L, L0) and torch.equal(m1.alpha, a0) and torch.equal(m1.lml_dev, l0), trial
