@@ -132,13 +132,14 @@ cross_cov_t_kernel(const double* __restrict__ X, long long N, Theta th, const do
   if (nr == 32) {
     // straight-line groups of eight independent evaluations (no exits inside: the chains interleave and the
     // constants stay in registers)
-#pragma unroll 1
-    for (int r0 = 0; r0 < 32; r0 += 8) {
+    double* dp = dst;                    // one walking pointer: no 64-bit multiply per store
+#pragma unroll
+    for (int r0 = 0; r0 < 32; r0 += 8) {   // unrolled too: the polynomial's constants are materialised once
       double v[8];
 #pragma unroll
       for (int r = 0; r < 8; r++) v[r] = rbf_t<D>(q[r0 + r], xi, th.sf2, etab);
 #pragma unroll
-      for (int r = 0; r < 8; r++) dst[(r0 + r) * ldks] = v[r];
+      for (int r = 0; r < 8; r++) { *dp = v[r]; dp += ldks; }
     }
   } else {
     for (int r = 0; r < nr; r++) dst[r * ldks] = rbf_t<D>(q[r], xi, th.sf2, etab);
