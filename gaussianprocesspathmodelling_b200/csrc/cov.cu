@@ -254,7 +254,7 @@ predict_mean_kernel(const double* __restrict__ X, long long N, Theta th, const d
     for (int e = tid; e < n * D; e += 256) { const int r = e / D, d = e % D; sx[r][d] = X[(i0 + r) * D + d] / th.l[d]; }
     for (int e = tid; e < n * RR; e += 256) { const int r = e / RR, k = e % RR; sa[r][k] = k < R ? alpha[(i0 + r) * R + k] : 0.0; }
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 8
     for (int i = 0; i < n; i++) {
       const double kv = rbf_t<D>(qs, sx[i], th.sf2, etab);
 #pragma unroll
