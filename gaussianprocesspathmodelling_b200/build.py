@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpmap_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "cov.cu", "potrf.cu", "solve.cu", "predict.cu", "batched.cu", "kmeans.cu", "grad.cu", "small.cu", "gemm_small.cu", "pathfit.cu", "fit.cu"]
+SOURCES = ["api.cu", "gemm.cu", "cov.cu", "potrf.cu", "solve.cu", "predict.cu", "batched.cu", "kmeans.cu", "grad.cu", "small.cu", "gemm_small.cu", "pathfit.cu", "fit.cu", "gemm_half.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -59,7 +59,7 @@ static const OptEntry kOptions[] = {
     {"no_fused_mean", &Options::no_fused_mean},   {"var_steps", &Options::var_steps},
     {"solve_steps", &Options::solve_steps},       {"grad_sweep", &Options::grad_sweep},
     {"no_path_fused", &Options::no_path_fused},   {"no_fused_solve", &Options::no_fused_solve},
-    {"path_fused", &Options::path_fused},
+    {"path_fused", &Options::path_fused},         {"no_half_tiles", &Options::no_half_tiles},
 };
 
 static void options_from_env(Options* o) {

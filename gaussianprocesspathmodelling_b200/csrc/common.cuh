@@ -69,6 +69,7 @@ struct Options {
   int no_separable = 0;      // grid queries through the pointwise kernels
   int no_small_fused = 0;    // short paths through the tiled pipeline
   int no_small_tiles = 0;    // no latency tile kernel
+  int no_half_tiles = 0;     // batched launches through the 128 x 128 tile kernel instead of the half-tile one
   int no_fused_fwd = 0;      // batched fits: separate forward substitution
   int no_fused_mean = 0;     // predict: separate mean kernel
   int var_steps = 0;         // variance: one launch per block column
@@ -91,7 +92,7 @@ struct gpm_handle_impl {
   int n_flags;                      //   (cleared on the stream at the start of every solve: graph-replay safe); a third
                                     //   array of n_flags publishes the per-block LML shares of the backward pass
   double* lml_part;                 // n_flags x 9 doubles: per-block shares of the log marginal likelihood
-  bool gemm_attr, potf2_attr, gemm_small_attr, gemm_strip_attr, pathfit_attr;       // opt-in shared-memory sizes set for this handle's device (function attributes are per device)
+  bool gemm_attr, potf2_attr, gemm_small_attr, gemm_strip_attr, pathfit_attr, gemm_half_attr;       // opt-in shared-memory sizes set for this handle's device (function attributes are per device)
 };
 
 // Entry points run on the handle's device whatever the caller's current device is, and restore it on return.

@@ -452,6 +452,7 @@ int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& 
   }
   const int total = gemm_grid_x(args);
   if (total <= 0 || batch <= 0) return 0;
+  if (gemm_half_eligible(h, args, batch)) return launch_gemm_half(h, args, batch, stream);   // whole-batch launches: half-tiles, two CTAs per SM
   if (gemm_small_eligible(h, args, batch)) return launch_gemm_small(h, args, stream);   // a fraction of a wave: latency kernel
   // tiles per CTA: minimise the makespan ceil(ceil(T/c)/slots)*c over c <= cmax, prefer the larger c
   const int cmax = args.max_tiles_per_cta > 0 ? args.max_tiles_per_cta : 16;

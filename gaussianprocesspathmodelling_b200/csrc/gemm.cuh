@@ -72,6 +72,9 @@ inline int gemm_grid_x(const GemmArgs& a) {
 // mapC describes the matrix args.C points into (used to prefetch C tiles by TMA when epi == EPI_SUB)
 bool gemm_small_eligible(const gpm_handle_impl* h, const GemmArgs& a, int batch);
 int launch_gemm_small(gpm_handle_impl* h, const GemmArgs& a, cudaStream_t stream);
+// large batches: 64 x 128 half-tiles, two CTAs per SM (gemm_half.cu)
+bool gemm_half_eligible(const gpm_handle_impl* h, const GemmArgs& a, int batch);
+int launch_gemm_half(gpm_handle_impl* h, const GemmArgs& a, int batch, cudaStream_t stream);
 
 int launch_gemm(gpm_handle_impl* h, const CUtensorMap& mapA, const CUtensorMap& mapB,
                 const CUtensorMap& mapC, const GemmArgs& args, int batch, cudaStream_t stream,

@@ -1,0 +1,269 @@
+// Half-tile variant of the FP64 tensor-core tile GEMM for the whole-batch launches of the batched fits (batch >= 32).
+//
+// gemm_nt_kernel gives a 128 x 128 tile to one CTA that owns the SM: its eight consumer warps leave the DMMA pipe idle
+// while they store a finished tile (and, in a panel solve, update the fused forward substitution), which at the
+// K = 128 / 256 contractions of an N = 512 path is 25 - 40 % of a tile (ncu on the six launches of a 4096-path call:
+// DMMA sub-pipe 58 - 62 % active in the panel solves, 75 - 78 % in the updates).  Here a CTA is four warps on 64 x 128
+// half-tiles (64 x 32 warp tiles, 128 accumulator registers: the same DMMA sequence per output element, so the
+// factor is bitwise the tile kernel's), 112 KB of shared memory, and TWO CTAs share an SM: one's epilogue runs under
+// the other's main loop, with no software pipelining.  There is no producer warp (ten warps per SM would cap the
+// kernel at 168 registers): thread 0 refills a ring stage when all four warps have released it, as in pathfit.cu.
+//
+// A CTA takes one 128 x 128 tile of the launch as two half-tiles in turn; the [128 x 16] B slabs are loaded once per
+// half (the second time from L2).  C -= A B^T prefetches the C half-tile by TMA under the main loop.
+#include "gemm.cuh"
+#include "halftile.cuh"
+
+namespace gpm {
+
+constexpr int GH_THREADS = 128;
+constexpr int GH_STAGES = 2;                             // (a third stage in the C space for the store launches measured 2 % slower)
+constexpr int GH_A_BYTES = 64 * SLAB_K * 8;              // 8 KB   [64 rows x 16] slab
+constexpr int GH_B_BYTES = NB * SLAB_K * 8;              // 16 KB  [128 rows x 16] slab
+constexpr int GH_STAGE_BYTES = GH_A_BYTES + GH_B_BYTES;  // 24 KB
+constexpr int GH_C_BYTES = 64 * NB * 8;                  // 64 KB: the C half-tile (C -= A B^T) / scratch of the fused forward substitution
+constexpr int GH_RING_OFF = GH_C_BYTES;
+constexpr int GH_BAR_OFF = GH_RING_OFF + GH_STAGES * GH_STAGE_BYTES;
+constexpr int GH_SMEM = GH_BAR_OFF + 64;
+
+__device__ __forceinline__ void gh_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GH_THREADS) : "memory"); }
+
+__global__ void __launch_bounds__(GH_THREADS, 2)
+gemm_nt_half_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const __grid_constant__ CUtensorMap mapC, const GemmArgs p) {
+  extern __shared__ __align__(1024) uint8_t gh_smem[];
+  const uint32_t base = smem_u32(gh_smem);
+  const uint32_t cbuf = base, ring = base + GH_RING_OFF;
+  const uint32_t bar_full = base + GH_BAR_OFF, bar_empty = bar_full + GH_STAGES * 8, bar_c = bar_empty + GH_STAGES * 8;
+  double* gen = reinterpret_cast<double*>(gh_smem);
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const long long bz = blockIdx.y;
+  if (tid == 0) {
+    for (int s = 0; s < GH_STAGES; s++) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 4); }
+    mbar_init(bar_c, 1);
+    fence_mbar_init();
+    prefetch_tmap(&mapA); prefetch_tmap(&mapB); prefetch_tmap(&mapC);
+  }
+  __syncthreads();
+  if ((base & 1023u) != 0) return;                         // the 128-byte swizzle needs a 1 KB-aligned window (never taken)
+
+  // the tile of this CTA (same enumeration as gemm_nt_kernel)
+  int ti, tj;
+  {
+    const int t = blockIdx.x;
+    if (p.tri) {
+      int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+      while ((i + 1) * (i + 2) / 2 <= t) i++;
+      while (i * (i + 1) / 2 > t) i--;
+      ti = i; tj = t - i * (i + 1) / 2;
+    } else {
+      ti = t % p.tiles_m; tj = t / p.tiles_m;
+    }
+  }
+  const int nslab = p.klen / SLAB_K;
+  const int a_row = p.a_row0 + ti * NB + (int)(bz * p.batch_a_rows);
+  const int b_row = p.b_row0 + tj * p.b_tile_rows + (int)(bz * p.batch_b_rows);
+  const long long c_row = p.c_row0 + (long long)ti * NB + bz * p.batch_c_rows;
+  const long long c_col = p.c_col0 + (long long)tj * NB;
+  const long long rows_end = p.c_rows_end + bz * p.batch_c_rows;
+  const bool sub = p.epi == EPI_SUB;
+  const bool diag = p.diag_lower && ti == tj;
+
+  uint32_t off[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) off[t] = frag_off(g, q, t);
+  const int cset[4] = {w, 7 - w, 8 + w, 15 - w};           // this warp's 8-column sub-tile columns (ascending)
+  uint32_t boff[4];
+#pragma unroll
+  for (int nt = 0; nt < 4; nt++) boff[nt] = (uint32_t)cset[nt] * 1024u;
+
+  // fused forward substitution: z_k of this matrix, staged once ([128][R] behind the partial sums in the C space)
+  const int R = p.rhs_R;
+  double* psm = gen;                                        // [64][4][R]
+  double* zsm = gen + 64 * 4 * 8;                           // [128][R]
+  if (p.rhs_r != nullptr) {
+    const double* zk = p.rhs_z + (p.rhs_z_row0 + bz * p.batch_rhs_rows) * R;
+    for (int idx = tid; idx < NB * R; idx += GH_THREADS) zsm[idx] = zk[idx];
+  }
+
+  constexpr int nst = GH_STAGES;
+  auto stage_addr = [&](int st) { return ring + st * GH_STAGE_BYTES; };
+  int sg = 0;                                               // slabs consumed so far (all threads agree)
+  int issued = 0;                                           // thread 0: slabs issued so far
+  uint32_t cpar = 0;
+  const int total_slabs = 2 * nslab;
+  auto issue = [&](int n) {                                  // thread 0: slab n of the CTA's stream (half = n / nslab)
+    const int h = n / nslab, s = n - h * nslab, st = n % nst;
+    const uint32_t dst = stage_addr(st), bar = bar_full + st * 8;
+    mbar_arrive_expect_tx(bar, GH_STAGE_BYTES);
+    tma_load_2d(dst, &mapA, p.a_col0 + s * SLAB_K, a_row + 64 * h, bar);
+    tma_load_2d(dst + GH_A_BYTES, &mapB, p.b_col0 + s * SLAB_K, b_row, bar);
+  };
+  if (tid == 0) { for (; issued < nst; issued++) issue(issued); }   // klen >= 32 (two slabs per half) is checked by the launcher
+
+  for (int h = 0; h < 2; h++) {
+    const long long row0 = c_row + 64 * h;
+    if (sub && tid == 0) {                                  // the C half-tile lands under the main loop
+      mbar_arrive_expect_tx(bar_c, GH_C_BYTES);
+#pragma unroll
+      for (int b = 0; b < NB / SLAB_K; b++)
+        tma_load_2d(cbuf + b * GH_A_BYTES, &mapC, (int)c_col + b * SLAB_K, (int)row0, bar_c);
+    }
+    double acc[8][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    for (int s = 0; s < nslab; s++, sg++) {
+      const int st = sg % nst;
+      mbar_wait(bar_full + st * 8, (sg / nst) & 1);
+      const uint32_t sa = stage_addr(st), sb = sa + GH_A_BYTES;
+      if (diag) {
+        switch (2 * w + h) {                                 // warp-uniform: lower-triangle shape of this warp's columns
+          case 0: pf_slab<PF_DIAG + 0>(acc, sa, sb, off, boff); break;
+          case 1: pf_slab<PF_DIAG + 1>(acc, sa, sb, off, boff); break;
+          case 2: pf_slab<PF_DIAG + 2>(acc, sa, sb, off, boff); break;
+          case 3: pf_slab<PF_DIAG + 3>(acc, sa, sb, off, boff); break;
+          case 4: pf_slab<PF_DIAG + 4>(acc, sa, sb, off, boff); break;
+          case 5: pf_slab<PF_DIAG + 5>(acc, sa, sb, off, boff); break;
+          case 6: pf_slab<PF_DIAG + 6>(acc, sa, sb, off, boff); break;
+          default: pf_slab<PF_DIAG + 7>(acc, sa, sb, off, boff); break;
+        }
+      } else if (p.tri_b) {
+        int dead = 0;                                       // B lower triangular: sub-tile column c needs slab s iff 2 s <= c
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) dead += (cset[nt] < 2 * s) ? 1 : 0;
+        switch (dead) {
+          case 0: pf_slab<PF_COLS + 0>(acc, sa, sb, off, boff); break;
+          case 1: pf_slab<PF_COLS + 1>(acc, sa, sb, off, boff); break;
+          case 2: pf_slab<PF_COLS + 2>(acc, sa, sb, off, boff); break;
+          case 3: pf_slab<PF_COLS + 3>(acc, sa, sb, off, boff); break;
+          default: break;
+        }
+      } else {
+        pf_slab<PF_FULL>(acc, sa, sb, off, boff);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + st * 8);
+      if (tid == 0 && issued < total_slabs) {               // refill the stage just released (by all four warps)
+        mbar_wait(bar_empty + st * 8, (sg / nst) & 1);
+        issue(issued);
+        issued++;
+      }
+    }
+    // ---------------- epilogue of the half-tile ----------------
+    if (sub) {
+      mbar_wait(bar_c, cpar);
+      cpar ^= 1u;
+#pragma unroll
+      for (int mt = 0; mt < 8; mt++) {
+        const long long row = row0 + mt * 8 + g;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+          const int c = cset[nt];
+          if (diag && c > mt + 8 * h) continue;             // above the diagonal of a symmetric tile: never read
+          const uint32_t addr = cbuf + (c >> 1) * GH_A_BYTES + (mt * 8 + g) * 128 + ((((c & 1) * 4 + q) ^ g) << 4);
+          double c0, c1;
+          asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c0), "=d"(c1) : "r"(addr));
+          const long long col = c_col + c * 8 + 2 * q;
+          if (row < rows_end) {
+            double* dst = p.C + row * p.ldc + col;
+            const double v0 = c0 - acc[mt][nt][0], v1 = c1 - acc[mt][nt][1];
+            if (col + 1 < p.c_cols_end) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            else if (col < p.c_cols_end) *dst = v0;
+          }
+        }
+      }
+      gh_sync();                                            // the C space may be refilled (next half's prefetch)
+    } else {
+#pragma unroll
+      for (int mt = 0; mt < 8; mt++) {
+        const long long row = row0 + mt * 8 + g;
+        if (row < rows_end) {
+          double* crow = p.C + row * p.ldc;
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            const long long col = c_col + cset[nt] * 8 + 2 * q;
+            double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
+            if (p.epi == EPI_NEG) { v0 = -v0; v1 = -v1; }
+            if (col + 1 < p.c_cols_end) *reinterpret_cast<double2*>(crow + col) = make_double2(v0, v1);
+            else if (col < p.c_cols_end) crow[col] = v0;
+          }
+        }
+      }
+      if (p.rhs_r != nullptr) {
+        // fused forward substitution: r_i -= L_ik z_k with the half-tile still in the accumulators; partial sums per
+        // (row, warp) through shared memory, added in a fixed order; one plain read-modify-write per residual entry
+        // (no other CTA of the launch touches these rows)
+        gh_sync();                                          // z_k is staged; the previous half's partial sums were consumed
+        for (int r = 0; r < R; r++) {
+          double zv[4][2], sum[8];
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            const int cl = cset[nt] * 8 + 2 * q;
+            zv[nt][0] = zsm[cl * R + r];
+            zv[nt][1] = zsm[(cl + 1) * R + r];
+          }
+#pragma unroll
+          for (int mt = 0; mt < 8; mt++) sum[mt] = 0.0;
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int mt = 0; mt < 8; mt++) {
+              sum[mt] = fma(acc[mt][nt][0], zv[nt][0], sum[mt]);
+              sum[mt] = fma(acc[mt][nt][1], zv[nt][1], sum[mt]);
+            }
+#pragma unroll
+          for (int mt = 0; mt < 8; mt++) sum[mt] += __shfl_xor_sync(0xffffffffu, sum[mt], 1);
+#pragma unroll
+          for (int mt = 0; mt < 8; mt++) sum[mt] += __shfl_xor_sync(0xffffffffu, sum[mt], 2);
+          if (q == 0) {
+#pragma unroll
+            for (int mt = 0; mt < 8; mt++) psm[((mt * 8 + g) * 4 + w) * R + r] = sum[mt];
+          }
+        }
+        gh_sync();
+        if (tid < 64) {
+          const long long row = p.rhs_r_row0 + (long long)ti * NB + 64 * h + tid;
+          if (row < p.rhs_rows_end) {
+            double* rr = p.rhs_r + (row + bz * p.batch_rhs_rows) * R;
+            for (int r = 0; r < R; r++)
+              rr[r] -= (psm[(tid * 4 + 0) * R + r] + psm[(tid * 4 + 1) * R + r]) +
+                       (psm[(tid * 4 + 2) * R + r] + psm[(tid * 4 + 3) * R + r]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// raw operand pointers present, a plain tile launch of a large batch: the half-tile kernel can take it
+bool gemm_half_eligible(const gpm_handle_impl* h, const GemmArgs& a, int batch) {
+  if (h->opt.no_half_tiles || batch < 32 || a.small_A == nullptr || a.small_B == nullptr) return false;
+  if (a.sweep_nblk > 0 || a.rowsq || a.kstart_mode || a.kend_mode || a.batch_cols) return false;
+  if (a.klen < 2 * SLAB_K || a.klen % SLAB_K != 0) return false;
+  if (a.epi != EPI_STORE && a.epi != EPI_SUB) return false;
+  if (a.rhs_r && (a.epi != EPI_STORE || a.rhs_R < 1 || a.rhs_R > 8)) return false;
+  if ((a.small_lda & 1) || (a.small_ldb & 1) || (a.ldc & 1)) return false;
+  return true;
+}
+
+int launch_gemm_half(gpm_handle_impl* h, const GemmArgs& a, int batch, cudaStream_t stream) {
+  if (!h->gemm_half_attr) {
+    GPM_CUDA(cudaFuncSetAttribute(gemm_nt_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GH_SMEM));
+    GPM_CUDA(cudaFuncSetAttribute(gemm_nt_half_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    h->gemm_half_attr = true;
+  }
+  CUtensorMap mapA, mapB, mapC;
+  int rc;
+  // [64 x 16] boxes over the A operand and over C, [128 x 16] boxes over B; the tensors span whole leading dimensions
+  if ((rc = make_tmap(h, &mapA, a.small_A, a.small_a_rows_end, a.small_lda, a.small_lda, 64))) return rc;
+  if ((rc = make_tmap(h, &mapB, a.small_B, a.small_b_rows_end, a.small_ldb, a.small_ldb, NB))) return rc;
+  if ((rc = make_tmap(h, &mapC, a.C, a.small_a_rows_end, a.ldc, a.ldc, 64))) return rc;
+  dim3 grid(gemm_grid_x(a), batch);
+  gemm_nt_half_kernel<<<grid, GH_THREADS, GH_SMEM, stream>>>(mapA, mapB, mapC, a);
+  GPM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace gpm
