@@ -152,6 +152,7 @@ gemm_nt_half_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
     }
     // ---------------- epilogue of the half-tile ----------------
+    const bool interior = row0 + 64 <= rows_end && c_col + NB <= p.c_cols_end;
     if (sub) {
       mbar_wait(bar_c, cpar);
       cpar ^= 1u;
@@ -166,9 +167,11 @@ gemm_nt_half_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           double c0, c1;
           asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c0), "=d"(c1) : "r"(addr));
           const long long col = c_col + c * 8 + 2 * q;
-          if (row < rows_end) {
+          const double v0 = c0 - acc[mt][nt][0], v1 = c1 - acc[mt][nt][1];
+          if (interior) {
+            *reinterpret_cast<double2*>(p.C + row * p.ldc + col) = make_double2(v0, v1);
+          } else if (row < rows_end) {
             double* dst = p.C + row * p.ldc + col;
-            const double v0 = c0 - acc[mt][nt][0], v1 = c1 - acc[mt][nt][1];
             if (col + 1 < p.c_cols_end) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
             else if (col < p.c_cols_end) *dst = v0;
           }
@@ -176,6 +179,17 @@ gemm_nt_half_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
       gh_sync();                                            // the C space may be refilled (next half's prefetch)
     } else {
+      if (p.epi == EPI_STORE && row0 + 64 <= rows_end && c_col + NB <= p.c_cols_end) {
+        // interior half-tile (all of them when N is a multiple of 128): no bounds tests, one walking pointer
+        double* crow = p.C + (row0 + g) * p.ldc + c_col + 2 * q;
+#pragma unroll
+        for (int mt = 0; mt < 8; mt++) {
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++)
+            *reinterpret_cast<double2*>(crow + cset[nt] * 8) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+          crow += 8 * p.ldc;
+        }
+      } else
 #pragma unroll
       for (int mt = 0; mt < 8; mt++) {
         const long long row = row0 + mt * 8 + g;
