@@ -69,6 +69,7 @@ struct Options {
   int no_separable = 0;      // grid queries through the pointwise kernels
   int no_small_fused = 0;    // short paths through the tiled pipeline
   int no_small_tiles = 0;    // no latency tile kernel
+  int no_split_column = 0;   // look-ahead Cholesky: update the next panel's whole column before its diagonal block (no split)
   int no_half_tiles = 0;     // batched launches through the 128 x 128 tile kernel instead of the half-tile one
   int no_fused_fwd = 0;      // batched fits: separate forward substitution
   int no_fused_mean = 0;     // predict: separate mean kernel

@@ -96,6 +96,28 @@ def test_potrf_lookahead_equals_plain():
     assert np.array_equal(L1, L2)                # same kernels, same order of arithmetic
 
 
+def test_potrf_split_column_lookahead_equals_plain():
+    # 24 <= blocks < 36: the look-ahead updates the next diagonal tile first and the rest of its column on the
+    # caller's stream (csrc/potrf.cu); same kernels on the same tiles, so the factor is bitwise the unsplit one
+    N = 3100                                     # 25 blocks, ragged last block
+    X, _, th = wl.single_path(N, seed=6, D=2)
+    Ko = gp_ref.cov(X, th)
+    L1, _, info = gpu_potrf(Ko)
+    assert info == 0
+    with _native.option("no_split_column", 1):
+        L2, _, _ = gpu_potrf(Ko)
+    with _native.option("no_lookahead", 1):
+        L3, _, _ = gpu_potrf(Ko)
+    assert np.array_equal(L1, L2) and np.array_equal(L1, L3)
+    assert np.abs(L1 @ L1.T - Ko).max() / np.abs(Ko).max() < 1e-14
+    # fused forward substitution rides along the split schedule too
+    Y = np.random.default_rng(7).standard_normal((N, 2))
+    m = GPmap.fit_gp(X, Y, theta=th)
+    with _native.option("no_split_column", 1):
+        m2 = GPmap.fit_gp(X, Y, theta=th)
+    assert torch.equal(m.alpha, m2.alpha) and torch.equal(m.lml_dev, m2.lml_dev)
+
+
 def test_potrf_reports_non_positive_pivot():
     A = np.eye(300); A[150, 150] = -1.0
     _, _, info = gpu_potrf(A)
