@@ -14,6 +14,9 @@
 #ifndef P2_MARK
 #define P2_MARK(slot)
 #endif
+#ifndef P2_MARK_LA
+#define P2_MARK_LA(p, e)
+#endif
 
 namespace gpm {
 
@@ -169,8 +172,37 @@ __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
       ta[e] = 0; tb[e] = 0;
     }
   }
+  // A warp that owns whole quads {(a, b), (TB-1-a, TB-1-b), (a, TB-1-b), (TB-1-a, b)} runs two tiles at a time: in
+  // phase 1 the two of a quad that share their column (same B operand, same contraction range), in phase 2 the two
+  // that share their row (same A operand) -- three operand loads per DMMA pair of a tile instead of four (the batched
+  // kernel is bound by shared-memory wavefronts, and these loads were 28 % of them) and four independent DMMA chains.
+  // Every tile still sees the same sequence of operations.
+  constexpr bool PAIRED = TB >= 2 && PER_WARP % 4 == 0 && P2_WARPS >= 8;   // (the four-warp group of pathfit.cu measured 2 % slower paired)
   // phase 1: T = L21 * X11   (X11 lower: contraction tiles kt >= tb)
-  if (active) {
+  if (PAIRED && active) {
+#pragma unroll
+    for (int e4 = 0; e4 < PER_WARP; e4 += 4)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; h2++) {
+        const int ea = e4 + h2, eb = e4 + 3 - h2;             // (m = 0, 3) and (m = 1, 2): same tb
+        const int t1 = t1s[ea];
+        const double* pa = sm + tile_base(t1 + TB + ta[ea], t1 + tb[ea]) + a_in;
+        const double* pa2 = sm + tile_base(t1 + TB + ta[eb], t1 + tb[ea]) + a_in;
+        const double* pb = sm + tile_base(t1 + tb[ea], t1 + tb[ea]) + b_in;
+        double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0, u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;
+        for (int kt = tb[ea]; kt < TB; kt++) {
+          const double b0 = pb[0], b1 = pb[32];
+          dmma(x0, x1, pa[0], b0);
+          dmma(u0, u1, pa2[0], b0);
+          dmma(y0, y1, pa[a4], b1);
+          dmma(v0, v1, pa2[a4], b1);
+          pa += 64; pa2 += 64;
+          pb += (t1 + kt + 1) * 64;
+        }
+        c0[ea] = x0 + y0; c1[ea] = x1 + y1;
+        c0[eb] = u0 + v0; c1[eb] = u1 + v1;
+      }
+  } else if (active) {
 #pragma unroll
     for (int e = 0; e < PER_WARP; e++) {
       const int t1 = t1s[e];
@@ -194,7 +226,30 @@ __device__ __forceinline__ void inv_level_dmma(double* sm, int warp, int lane) {
   }
   p2_sync<P2_WARPS * 32, BAR>();
   // phase 2: X21 = -X22 * T   (X22 lower: contraction tiles kt <= ta)
-  if (active) {
+  if (PAIRED && active) {
+#pragma unroll
+    for (int e4 = 0; e4 < PER_WARP; e4 += 4)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; h2++) {
+        const int ea = e4 + h2, eb = e4 + 2 + h2;             // (m = 0, 2) and (m = 1, 3): same ta
+        const int t1 = t1s[ea];
+        const double* pa = sm + tile_base(t1 + TB + ta[ea], t1 + TB) + a_in;
+        const double* pb = sm + tile_base(t1 + TB, t1 + tb[ea]) + b_in;
+        const double* pb2 = sm + tile_base(t1 + TB, t1 + tb[eb]) + b_in;
+        double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0, u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;
+        for (int kt = 0; kt <= ta[ea]; kt++) {
+          const double a0 = pa[0], a1 = pa[a4];
+          dmma(x0, x1, a0, pb[0]);
+          dmma(u0, u1, a0, pb2[0]);
+          dmma(y0, y1, a1, pb[32]);
+          dmma(v0, v1, a1, pb2[32]);
+          pa += 64;
+          pb += (t1 + TB + kt + 1) * 64; pb2 += (t1 + TB + kt + 1) * 64;
+        }
+        c0[ea] = -(x0 + y0); c1[ea] = -(x1 + y1);
+        c0[eb] = -(u0 + v0); c1[eb] = -(u1 + v1);
+      }
+  } else if (active) {
 #pragma unroll
     for (int e = 0; e < PER_WARP; e++) {
       const int t1 = t1s[e];
@@ -256,19 +311,27 @@ __device__ __forceinline__ void potf2_factor(double* sm, int tid, int nv, long l
     // (1) panel solve by forward substitution against the factored 8x8 diagonal tile (l8, rd), one thread
     //     per row below it:  x_c = (a_c - sum_{k<c} x_k L8[c][k]) / L8[c][c]
     if (tid < NB && tid >= c0 + 8) {
+      // the row as four 16-byte pairs (a pair keeps its order under the in-tile swizzle): the eight rows of a tile are
+      // 64 bytes apart, so 8-byte accesses run at eight wavefronts per instruction and 16-byte ones at two per quarter
+      // warp -- half the shared-memory traffic of this step (the batched kernel is bound by shared-memory wavefronts)
       double x[8];
       double* row = sm + tile_base(tid >> 3, p) + (tid & 7) * 8;
       const int sw = ((tid >> 1) & 1) << 2;
 #pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(row + (c ^ sw));
+        x[c] = v.x; x[c + 1] = v.y;
+      }
+#pragma unroll
       for (int c = 0; c < 8; c++) {
-        double v = row[c ^ sw];
+        double v = x[c];
 #pragma unroll
         for (int k = 0; k < 8; k++)
           if (k < c) v = fma(-x[k], l8[c * (c + 1) / 2 + k], v);
         x[c] = v * rd[c0 + c];
       }
 #pragma unroll
-      for (int c = 0; c < 8; c++) row[c ^ sw] = x[c];
+      for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(row + (c ^ sw)) = make_double2(x[c], x[c + 1]);
     }
     p2_sync<P2_THREADS, BAR>();
     P2_MARK(3 + 3 * p)
@@ -288,50 +351,54 @@ __device__ __forceinline__ void potf2_factor(double* sm, int tid, int nv, long l
       *cp = c;
       __syncwarp();
       if (lane == 0) {
+        P2_MARK_LA(p, 0)
         const int bad = chol8_tile(sm, tile_base(rbt, rbt), l8, rd + c0 + 8);
         if (bad && c0 + 8 + bad - 1 < nv) atomicCAS(info, 0, (int)(r0 + c0 + 8 + bad));
+        P2_MARK_LA(p, 1)
       }
     } else if (upd_warp) {
-      // contiguous chunk of tiles per warp: consecutive tiles share their row, so the A fragments are
-      // reloaded only at a row change and the C / B addresses advance by constant strides
+      // contiguous chunk of tiles per warp, walked row by row: inside a row the A fragments stay in registers and the
+      // C / B addresses advance by constant / linearly growing strides (packed rows), two tiles (two independent
+      // DMMA chains) per iteration and no per-tile branching -- the first version of this loop spent 41 instructions
+      // per tile on its bookkeeping and ran at a third of the DMMA rate of its scheduler (ncu instruction counts,
+      // clock stamps: 600 cycles per pair of tiles)
       const int per = (T - 1 + NU - 1) / NU;
       int t = 1 + uidx * per;
-      const int tend = min(T, t + per);
-      if (t < tend) {
+      int left = min(T, t + per) - t;
+      if (left > 0) {
         int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
         while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
         while (ti * (ti + 1) / 2 > t) ti--;
         int tj = t - ti * (ti + 1) / 2;
-        const int bb0 = tile_base(rbt, p) + x_in;
-        int cb = tile_base(rbt + ti, rbt + tj) + c_in;      // C fragment of tile (ti, tj)
-        int bb = tile_base(rbt + tj, p) + x_in;             // B fragment: panel rows of tile-row tj
-        double a0, a1;
-        { const double* xa = sm + tile_base(rbt + ti, p) + x_in; a0 = -xa[0]; a1 = -xa[x4]; }
-        auto step = [&]() {
-          tj++; cb += 64; bb += (rbt + tj) * 64;
-          if (tj > ti) {
-            ti++; tj = 0;
-            cb = tile_base(rbt + ti, rbt) + c_in; bb = bb0;
-            const double* xa = sm + tile_base(rbt + ti, p) + x_in; a0 = -xa[0]; a1 = -xa[x4];
+        int arow = tile_base(rbt + ti, p) + x_in;           // panel fragment of tile-row ti (the A operand)
+        while (left > 0) {
+          const int n = min(left, ti + 1 - tj);             // tiles of this row inside the chunk
+          const double a0 = -sm[arow], a1 = -sm[arow + x4];
+          int cb = tile_base(rbt + ti, rbt + tj) + c_in;    // C fragment of tile (ti, tj); +64 per tile
+          int bb = tile_base(rbt + tj, p) + x_in;           // B fragment: panel rows of tile-row tj; next row: + bstep
+          int bstep = (rbt + tj + 1) * 64;
+          int j = 0;
+          for (; j + 1 < n; j += 2) {
+            double2 cA = *reinterpret_cast<const double2*>(sm + cb), cB = *reinterpret_cast<const double2*>(sm + cb + 64);
+            const double bA0 = sm[bb], bA1 = sm[bb + x4], bB0 = sm[bb + bstep], bB1 = sm[bb + bstep + x4];
+            dmma(cA.x, cA.y, a0, bA0);
+            dmma(cB.x, cB.y, a0, bB0);
+            dmma(cA.x, cA.y, a1, bA1);
+            dmma(cB.x, cB.y, a1, bB1);
+            *reinterpret_cast<double2*>(sm + cb) = cA;
+            *reinterpret_cast<double2*>(sm + cb + 64) = cB;
+            cb += 128; bb += 2 * bstep + 64; bstep += 128;
           }
-        };
-        while (t < tend) {
-          const bool two = t + 1 < tend;
-          const int cbA = cb, bbA = bb;
-          const double aA0 = a0, aA1 = a1;
-          if (two) step();
-          const int cbB = cb, bbB = bb;
-          const double aB0 = a0, aB1 = a1;
-          if (t + 2 < tend) step();
-          t += 2;
-          double2 cA = *reinterpret_cast<const double2*>(sm + cbA), cB = *reinterpret_cast<const double2*>(sm + cbB);
-          const double bA0 = sm[bbA], bA1 = sm[bbA + x4], bB0 = sm[bbB], bB1 = sm[bbB + x4];
-          dmma(cA.x, cA.y, aA0, bA0);
-          dmma(cB.x, cB.y, aB0, bB0);
-          dmma(cA.x, cA.y, aA1, bA1);
-          dmma(cB.x, cB.y, aB1, bB1);
-          *reinterpret_cast<double2*>(sm + cbA) = cA;
-          if (two) *reinterpret_cast<double2*>(sm + cbB) = cB;
+          if (j < n) {
+            double2 cA = *reinterpret_cast<const double2*>(sm + cb);
+            const double bA0 = sm[bb], bA1 = sm[bb + x4];
+            dmma(cA.x, cA.y, a0, bA0);
+            dmma(cA.x, cA.y, a1, bA1);
+            *reinterpret_cast<double2*>(sm + cb) = cA;
+          }
+          left -= n;
+          ti++; tj = 0;
+          arow += (rbt + ti) * 64;                           // tile_base(r + 1, p) - tile_base(r, p) = (r + 1) 64
         }
       }
     }

@@ -19,12 +19,14 @@
 #ifdef GPM_POTF2_TIMING
 // phase stamps of CTA 0 (cycles): the branch on a value loaded from shared memory after the barrier keeps
 // the clock read behind the barrier's completion (BAR.SYNC.DEFER_BLOCKING lets independent work issue early)
-namespace gpm { __device__ long long g_p2_marks[64]; }
+namespace gpm { __device__ long long g_p2_marks[128]; }
 #define P2_MARK(slot)                                                                        \
   if (tid == 0 && blockIdx.x == 0) {                                                         \
     const double pv_ = *reinterpret_cast<volatile double*>(sm + gpm::PACKED + 63);           \
     if (__double_as_longlong(pv_) != 0x7ff8dead0000beefLL) gpm::g_p2_marks[slot] = clock64(); \
   }
+// the look-ahead warp's lane 0 around the 8x8 factorisation of the next diagonal tile (panel p): slots 64+2p, 65+2p
+#define P2_MARK_LA(p, e) if (blockIdx.x == 0) gpm::g_p2_marks[64 + 2 * (p) + (e)] = clock64();
 #endif
 #include "potf2.cuh"
 
@@ -55,21 +57,35 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
 #ifdef GPM_POTF2_TIMING
   if (tid == 0 && blockIdx.x == 0) g_p2_marks[58] = clock64();
 #endif
-  // load the lower triangle as 16-byte pairs (LU independent loads in flight per thread); identity padding
-  // beyond nv.  A pair never straddles a tile and keeps its order under the in-tile swizzle (bit 2 only).
-  constexpr int LU = P2_THREADS == 256 ? 8 : 16;   // loads in flight per thread (register budget)
-  for (int u0 = 0; u0 < NB * NB / 2 / P2_THREADS; u0 += LU) {
-    double2 v[LU];
+  // Block <-> global memory copies go tile by tile: a warp moves one 8 x 8 tile per instruction (lane = row g, column
+  // pair 2q: 16 bytes), which is 512 contiguous bytes of the packed block -- conflict-free in shared memory (a warp
+  // along a matrix row puts its eight tiles on the same 64 bytes of banks: twice the wavefronts) -- and eight 64-byte
+  // row segments in global memory.  A pair never straddles a tile and keeps its order under the in-tile swizzle.
+  constexpr int P2_WARPS = P2_THREADS / 32;
+  const int warp = tid >> 5, lg = (tid & 31) >> 2, lq = (tid & 3) * 2;
+  const int inoff = in_tile(lg, lq);
+  // load the lower triangle (LU independent loads in flight per thread); identity padding beyond nv
+  constexpr int LU = 9;                            // 136 tiles: 17 per warp with 8 warps (9 + 8), at most 9 with 16
+  {
+    int ti = 0, tj = warp;
+    while (tj > ti) { tj -= ti + 1; ti++; }
+    for (int t0 = warp; t0 < PACKED / 64; t0 += LU * P2_WARPS) {
+      double2 v[LU];
+      int ti_u = ti, tj_u = tj;
 #pragma unroll
-    for (int u = 0; u < LU; u++) {
-      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 6, c = (idx & 63) * 2;
-      if (i < nv && c <= i) v[u] = *reinterpret_cast<const double2*>(K + (r0 + i) * ldk + r0 + c);
-      else v[u] = make_double2((i == c && i >= nv) ? 1.0 : 0.0, (i == c + 1 && i >= nv) ? 1.0 : 0.0);
-    }
+      for (int u = 0; u < LU; u++) {
+        const int i = ti_u * 8 + lg, c = tj_u * 8 + lq;
+        if (t0 + u * P2_WARPS < PACKED / 64) {
+          if (i < nv && c <= i) v[u] = *reinterpret_cast<const double2*>(K + (r0 + i) * ldk + r0 + c);
+          else v[u] = make_double2((i == c && i >= nv) ? 1.0 : 0.0, (i == c + 1 && i >= nv) ? 1.0 : 0.0);
+        }
+        tj_u += P2_WARPS;
+        while (tj_u > ti_u) { tj_u -= ti_u + 1; ti_u++; }
+      }
 #pragma unroll
-    for (int u = 0; u < LU; u++) {
-      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 6, c = (idx & 63) * 2;
-      if ((c >> 3) <= (i >> 3)) *reinterpret_cast<double2*>(sm + toff(i, c)) = v[u];
+      for (int u = 0; u < LU; u++)
+        if (t0 + u * P2_WARPS < PACKED / 64) *reinterpret_cast<double2*>(sm + (t0 + u * P2_WARPS) * 64 + inoff) = v[u];
+      ti = ti_u; tj = tj_u;
     }
   }
   if (rhs_r != nullptr)     // r_k is final before this launch: stage it now, its latency hides behind the factorisation
@@ -80,16 +96,19 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
 
   potf2_factor<P2_THREADS, 0>(sm, tid, nv, r0, info);
 
-  // ---- write L_kk (lower part, valid rows), 16-byte pairs ----
-  for (int u0 = 0; u0 < NB * NB / 2 / P2_THREADS; u0 += 16) {
-#pragma unroll
-    for (int u = 0; u < 16; u++) {
-      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 6, c = (idx & 63) * 2;
+  // ---- write L_kk (lower part, valid rows), tile by tile ----
+  {
+    int ti = 0, tj = warp;
+    while (tj > ti) { tj -= ti + 1; ti++; }
+    for (int t = warp; t < PACKED / 64; t += P2_WARPS) {
+      const int i = ti * 8 + lg, c = tj * 8 + lq;
       if (i < nv && c <= i) {
-        const double2 v = *reinterpret_cast<const double2*>(sm + toff(i, c));
+        const double2 v = *reinterpret_cast<const double2*>(sm + t * 64 + inoff);
         double* dst = K + (r0 + i) * ldk + r0 + c;
         if (c < i) *reinterpret_cast<double2*>(dst) = v; else *dst = v.x;
       }
+      tj += P2_WARPS;
+      while (tj > ti) { tj -= ti + 1; ti++; }
     }
   }
   P2_MARK(50)
@@ -99,13 +118,13 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
     potf2_fwd_z<P2_THREADS, 0, true>(sm, tid, nv, rhs_r + (blockIdx.x * batch_rhs_rows + r0) * R,
                                rhs_z + (blockIdx.x * batch_rhs_rows + r0) * R, R);
   P2_MARK(57)
-  for (int u0 = 0; u0 < NB * NB / 2 / P2_THREADS; u0 += 16) {
-#pragma unroll
-    for (int u = 0; u < 16; u++) {
-      const int idx = tid + P2_THREADS * (u0 + u), i = idx >> 6, c = (idx & 63) * 2;
-      reinterpret_cast<double2*>(invD)[idx] =
-          ((c >> 3) <= (i >> 3)) ? *reinterpret_cast<const double2*>(sm + toff(i, c)) : make_double2(0.0, 0.0);
-    }
+  // the inverse, all 16 x 16 tiles (zeros above the diagonal), tile by tile
+#pragma unroll 4
+#pragma unroll 4
+  for (int t = warp; t < NT8 * NT8; t += P2_WARPS) {
+    const int ti = t >> 4, tj = t & 15;
+    const double2 v = tj <= ti ? *reinterpret_cast<const double2*>(sm + tile_base(ti, tj) + inoff) : make_double2(0.0, 0.0);
+    *reinterpret_cast<double2*>(invD + (ti * 8 + lg) * NB + tj * 8 + lq) = v;
   }
   P2_MARK(56)
 }
@@ -317,7 +336,7 @@ using namespace gpm;
 
 #ifdef GPM_POTF2_TIMING
 extern "C" int gpm_debug_potf2_marks(long long* out) {
-  return (int)cudaMemcpyFromSymbol(out, g_p2_marks, sizeof(long long) * 64);
+  return (int)cudaMemcpyFromSymbol(out, g_p2_marks, sizeof(long long) * 128);
 }
 #endif
 

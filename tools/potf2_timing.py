@@ -14,7 +14,7 @@ else:
     X, Y, th = wl.single_path(N, 4, 2, 2)
     for _ in range(2): GPmap.fit_gp(X, Y, theta=th)
 torch.cuda.synchronize()
-buf = (C.c_longlong * 64)()
+buf = (C.c_longlong * 128)()
 lib.gpm_debug_potf2_marks(buf)
 m = np.frombuffer(buf, dtype=np.int64).astype(np.float64)
 print("load %.0f, first barrier %.0f, first 8x8 factor %.0f" % (m[0] - m[58], m[1] - m[0], m[2] - m[1]))
@@ -22,6 +22,8 @@ fw = np.array([m[3 + 3 * p] - m[2 + 3 * p] for p in range(16)])
 up = np.array([m[4 + 3 * p] - m[3 + 3 * p] for p in range(15)])
 print("fwdsub  per panel:", fw.astype(int).tolist(), "sum", int(fw.sum()))
 print("update+lookahead factor per panel:", up.astype(int).tolist(), "sum", int(up.sum()))
+print("look-ahead lane: barrier -> start of the 8x8 factorisation:", [int(m[64 + 2 * p] - m[3 + 3 * p]) for p in range(15)])
+print("look-ahead lane: 8x8 factorisation:", [int(m[65 + 2 * p] - m[64 + 2 * p]) for p in range(15)])
 print("write L %.0f | inv level0 %.0f | levels 8/16/32/64: %.0f %.0f %.0f %.0f | fused z %.0f | store inv %.0f" % (
     m[50] - m[48], m[51] - m[50], m[52] - m[51], m[53] - m[52], m[54] - m[53], m[55] - m[54], m[57] - m[55], m[56] - m[57]))
 print("total from end of load to end: %.0f cycles" % (m[56] - m[0]))
