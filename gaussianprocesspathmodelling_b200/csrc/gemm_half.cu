@@ -17,7 +17,7 @@
 namespace gpm {
 
 constexpr int GH_THREADS = 128;
-constexpr int GH_STAGES = 2;                             // (a third stage in the C space for the store launches measured 2 % slower)
+constexpr int GH_STAGES = 2;                             // (deeper rings in the free part of the C space of the plain-store launches: no gain, tools/ab_half.py history in DESIGN.md)
 constexpr int GH_A_BYTES = 64 * SLAB_K * 8;              // 8 KB   [64 rows x 16] slab
 constexpr int GH_B_BYTES = NB * SLAB_K * 8;              // 16 KB  [128 rows x 16] slab
 constexpr int GH_STAGE_BYTES = GH_A_BYTES + GH_B_BYTES;  // 24 KB
@@ -27,6 +27,9 @@ constexpr int GH_BAR_OFF = GH_RING_OFF + GH_STAGES * GH_STAGE_BYTES;
 constexpr int GH_SMEM = GH_BAR_OFF + 64;
 
 __device__ __forceinline__ void gh_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GH_THREADS) : "memory"); }
+__device__ __forceinline__ void gh_cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 
 __global__ void __launch_bounds__(GH_THREADS, 2)
 gemm_nt_half_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -77,13 +80,24 @@ gemm_nt_half_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
   for (int nt = 0; nt < 4; nt++) boff[nt] = (uint32_t)cset[nt] * 1024u;
 
-  // fused forward substitution: z_k of this matrix, staged once ([128][R] behind the partial sums in the C space)
+  // fused forward substitution: z_k of this matrix and the residual rows of this tile come in by cp.async while the
+  // main loop runs (no registers, no exposed global round trip in the epilogue: with staged loads there the panel
+  // launches ran their DMMA pipe 63 % active); scratch in the C space (unused by a plain-store launch):
+  // partial sums [64][4][R] | z_k [128][R] | residual rows [128][R]
   const int R = p.rhs_R;
-  double* psm = gen;                                        // [64][4][R]
-  double* zsm = gen + 64 * 4 * 8;                           // [128][R]
+  double* psm = gen;
+  double* zsm = gen + 256 * R;
+  double* rsm = zsm + NB * R;
   if (p.rhs_r != nullptr) {
     const double* zk = p.rhs_z + (p.rhs_z_row0 + bz * p.batch_rhs_rows) * R;
-    for (int idx = tid; idx < NB * R; idx += GH_THREADS) zsm[idx] = zk[idx];
+    const long long rrow0 = p.rhs_r_row0 + (long long)ti * NB;
+    const double* rk = p.rhs_r + (rrow0 + bz * p.batch_rhs_rows) * R;
+    const long long nr = p.rhs_rows_end - rrow0;           // valid residual rows of this tile (>= 1)
+    for (int idx = tid; idx < NB * R; idx += GH_THREADS) {
+      gh_cp_async8(smem_u32(zsm + idx), zk + idx);
+      if (idx < nr * R) gh_cp_async8(smem_u32(rsm + idx), rk + idx);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
   constexpr int nst = GH_STAGES;
@@ -209,7 +223,8 @@ gemm_nt_half_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         // fused forward substitution: r_i -= L_ik z_k with the half-tile still in the accumulators; partial sums per
         // (row, warp) through shared memory, added in a fixed order; one plain read-modify-write per residual entry
         // (no other CTA of the launch touches these rows)
-        gh_sync();                                          // z_k is staged; the previous half's partial sums were consumed
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        gh_sync();                                          // z_k and the residual rows have landed; the previous half's partial sums were consumed
         for (int r = 0; r < R; r++) {
           double zv[4][2], sum[8];
 #pragma unroll
@@ -242,8 +257,8 @@ gemm_nt_half_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           if (row < p.rhs_rows_end) {
             double* rr = p.rhs_r + (row + bz * p.batch_rhs_rows) * R;
             for (int r = 0; r < R; r++)
-              rr[r] -= (psm[(tid * 4 + 0) * R + r] + psm[(tid * 4 + 1) * R + r]) +
-                       (psm[(tid * 4 + 2) * R + r] + psm[(tid * 4 + 3) * R + r]);
+              rr[r] = rsm[(64 * h + tid) * R + r] - ((psm[(tid * 4 + 0) * R + r] + psm[(tid * 4 + 1) * R + r]) +
+                                                     (psm[(tid * 4 + 2) * R + r] + psm[(tid * 4 + 3) * R + r]));
           }
         }
       }
