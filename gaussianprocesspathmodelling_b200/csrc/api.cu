@@ -60,6 +60,7 @@ static const OptEntry kOptions[] = {
     {"solve_steps", &Options::solve_steps},       {"grad_sweep", &Options::grad_sweep},
     {"no_path_fused", &Options::no_path_fused},   {"no_fused_solve", &Options::no_fused_solve},
     {"path_fused", &Options::path_fused},         {"no_half_tiles", &Options::no_half_tiles},
+    {"half_warps", &Options::half_warps},          {"half_stages", &Options::half_stages},
     {"no_split_column", &Options::no_split_column},
 };
 

@@ -70,6 +70,8 @@ struct Options {
   int no_small_fused = 0;    // short paths through the tiled pipeline
   int no_small_tiles = 0;    // no latency tile kernel
   int no_split_column = 0;   // look-ahead Cholesky: update the next panel's whole column before its diagonal block (no split)
+  int half_stages = 0;       // half-tile kernel: cap on the ring depth of the plain-store launches (0 = auto: 4, or 3 with more than 4 right-hand sides)
+  int half_warps = 8;        // half-tile kernel: warps per CTA (8: 32 x 32 warp tiles, four warps per scheduler; 4: 64 x 32)
   int no_half_tiles = 0;     // batched launches through the 128 x 128 tile kernel instead of the half-tile one
   int no_fused_fwd = 0;      // batched fits: separate forward substitution
   int no_fused_mean = 0;     // predict: separate mean kernel

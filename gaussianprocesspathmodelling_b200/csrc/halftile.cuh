@@ -29,23 +29,29 @@ __host__ __device__ constexpr bool pf_col_live(int nt) {
   return false;
 }
 
-template <int SHAPE>
-__device__ __forceinline__ void pf_slab(double (&acc)[8][4][2], uint32_t sa, uint32_t sb, const uint32_t (&off)[4],
+// MT0, NMT: the sub-tile rows [MT0, MT0 + NMT) of the 64-row half-tile this warp owns (all eight with four warps per
+// half-tile; four with eight warps, gemm_half.cu); acc is indexed by the local row mt - MT0.
+template <int SHAPE, int MT0 = 0, int NMT = 8>
+__device__ __forceinline__ void pf_slab(double (&acc)[NMT][4][2], uint32_t sa, uint32_t sb, const uint32_t (&off)[4],
                                         const uint32_t (&boff)[4]) {
 #pragma unroll
   for (int k4 = 0; k4 < 4; k4++) {
-    double a[8], b[4];
+    double a[NMT], b[4];
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++)
-      if (pf_row_live<SHAPE>(mt)) a[mt] = lds_f64(sa + mt * 1024 + off[k4]);
+    for (int mt = 0; mt < NMT; mt++)
+      if (pf_row_live<SHAPE>(MT0 + mt)) a[mt] = lds_f64(sa + (MT0 + mt) * 1024 + off[k4]);
 #pragma unroll
-    for (int nt = 0; nt < 4; nt++)
-      if (pf_col_live<SHAPE>(nt)) b[nt] = lds_f64(sb + boff[nt] + off[k4]);
+    for (int nt = 0; nt < 4; nt++) {
+      bool live = false;
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++)
+      for (int mt = 0; mt < NMT; mt++) live = live || pf_live<SHAPE>(MT0 + mt, nt);
+      if (live) b[nt] = lds_f64(sb + boff[nt] + off[k4]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < NMT; mt++)
 #pragma unroll
       for (int nt = 0; nt < 4; nt++)
-        if (pf_live<SHAPE>(mt, nt)) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        if (pf_live<SHAPE>(MT0 + mt, nt)) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
   }
 }
 
