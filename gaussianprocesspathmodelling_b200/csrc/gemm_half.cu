@@ -3,21 +3,23 @@
 // gemm_nt_kernel gives a 128 x 128 tile to one CTA that owns the SM: its eight consumer warps leave the DMMA pipe idle
 // while they store a finished tile (and, in a panel solve, update the fused forward substitution), which at the
 // K = 128 / 256 contractions of an N = 512 path is 25 - 40 % of a tile (ncu on the six launches of a 4096-path call:
-// DMMA sub-pipe 58 - 62 % active in the panel solves, 75 - 78 % in the updates).  Here a CTA is four warps on 64 x 128
-// half-tiles (64 x 32 warp tiles, 128 accumulator registers: the same DMMA sequence per output element, so the
-// factor is bitwise the tile kernel's), 112 KB of shared memory, and TWO CTAs share an SM: one's epilogue runs under
-// the other's main loop, with no software pipelining.  There is no producer warp (ten warps per SM would cap the
-// kernel at 168 registers): thread 0 refills a ring stage when all four warps have released it, as in pathfit.cu.
+// DMMA sub-pipe 58 - 62 % active in the panel solves, 75 - 78 % in the updates).  Here a CTA works on 64 x 128
+// half-tiles with 112 KB of shared memory and TWO CTAs share an SM, so that one's epilogue can run under the other's
+// main loop; the DMMA sequence per output element is the tile kernel's, so the factor is bitwise the same.  Eight warps
+// per CTA (32 x 32 warp tiles, 64 accumulator registers; four warps per scheduler) by default: two warps per scheduler
+// (the first version: four warps on 64 x 32 warp tiles) do not keep its DMMA pipe busy.  There is no
+// producer warp: thread 0 refills a ring stage when all warps have released it, as in pathfit.cu.
 //
 // A CTA takes one 128 x 128 tile of the launch as two half-tiles in turn; the [128 x 16] B slabs are loaded once per
-// half (the second time from L2).  C -= A B^T prefetches the C half-tile by TMA under the main loop.
+// half (the second time from L2).  C -= A B^T prefetches the C half-tile by TMA under the main loop (two-stage ring);
+// plain-store launches use the free C space for two more stages.
 #include "gemm.cuh"
 #include "halftile.cuh"
 
 namespace gpm {
 
 constexpr int GH_THREADS = 128;                          // four-warp variant; the eight-warp one runs 256
-constexpr int GH_STAGES = 2;                             // (deeper rings in the free part of the C space of the plain-store launches: no gain, tools/ab_half.py history in DESIGN.md)
+constexpr int GH_STAGES = 2;                             // ring stages of their own (plain-store launches add up to two in the C space)
 constexpr int GH_A_BYTES = 64 * SLAB_K * 8;              // 8 KB   [64 rows x 16] slab
 constexpr int GH_B_BYTES = NB * SLAB_K * 8;              // 16 KB  [128 rows x 16] slab
 constexpr int GH_STAGE_BYTES = GH_A_BYTES + GH_B_BYTES;  // 24 KB
