@@ -61,7 +61,7 @@ static const OptEntry kOptions[] = {
     {"no_path_fused", &Options::no_path_fused},   {"no_fused_solve", &Options::no_fused_solve},
     {"path_fused", &Options::path_fused},         {"no_half_tiles", &Options::no_half_tiles},
     {"half_warps", &Options::half_warps},          {"half_stages", &Options::half_stages},
-    {"no_split_column", &Options::no_split_column},
+    {"no_split_column", &Options::no_split_column}, {"no_scratch_factor", &Options::no_scratch_factor},
 };
 
 static void options_from_env(Options* o) {

@@ -113,7 +113,10 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
   if (solve_paths_supported(N) && !h->opt.no_fused_fwd) {
     double* zf = invD + (long long)B * nblk * NB * NB + (long long)B * 8;
     GPM_CUDA(cudaMemcpyAsync(alpha, Yb, (size_t)B * N * R * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    if ((rc = potrf_blocked(h, Kb, N, np, invD, info, (int)B, np, st, alpha, zf, R, N))) return rc;
+    h->scratch_factor = !h->opt.no_scratch_factor;      // nothing below reads L_kk beyond its diagonal (the backward pass uses inv(L_kk))
+    rc = potrf_blocked(h, Kb, N, np, invD, info, (int)B, np, st, alpha, zf, R, N);
+    h->scratch_factor = false;
+    if (rc) return rc;
     return solve_paths(Kb, N, np, invD, Yb, alpha, lml, R, (int)B, np * np, (long long)nblk * NB * NB, N * R, st, zf);
   }
   if ((rc = potrf_blocked(h, Kb, N, np, invD, info, (int)B, np, st, nullptr, nullptr, 0, 0))) return rc;

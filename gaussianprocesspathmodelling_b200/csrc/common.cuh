@@ -74,6 +74,7 @@ struct Options {
   int half_warps = 8;        // half-tile kernel: warps per CTA (8: 32 x 32 warp tiles, four warps per scheduler; 4: 64 x 32)
   int no_half_tiles = 0;     // batched launches through the 128 x 128 tile kernel instead of the half-tile one
   int no_fused_fwd = 0;      // batched fits: separate forward substitution
+  int no_scratch_factor = 0; // batched fits: potf2 stores the whole lower triangle of L_kk although only its diagonal is read afterwards
   int no_fused_mean = 0;     // predict: separate mean kernel
   int var_steps = 0;         // variance: one launch per block column
   int solve_steps = 0;       // solves: one launch per block step
@@ -95,6 +96,8 @@ struct gpm_handle_impl {
   int n_flags;                      //   (cleared on the stream at the start of every solve: graph-replay safe); a third
                                     //   array of n_flags publishes the per-block LML shares of the backward pass
   double* lml_part;                 // n_flags x 9 doubles: per-block shares of the log marginal likelihood
+  bool scratch_factor;              // set by gpm_fit_batched around its factorisation: L is scratch there (only alpha and the LML leave),
+                                    //   so potf2 stores just the diagonal 8 x 8 tiles of L_kk (the log-determinant reads the diagonal)
   bool gemm_attr, potf2_attr, gemm_small_attr, gemm_strip_attr, pathfit_attr, gemm_half_attr;       // opt-in shared-memory sizes set for this handle's device (function attributes are per device)
 };
 

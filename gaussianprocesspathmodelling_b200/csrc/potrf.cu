@@ -45,7 +45,8 @@ template <int P2_THREADS>
 __global__ void __launch_bounds__(P2_THREADS, P2_THREADS == 256 ? 3 : 1)
 potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, double* __restrict__ invD,
                  int* __restrict__ info, long long batch_k, long long batch_inv,
-                 const double* rhs_r, double* rhs_z, int R, long long batch_rhs_rows) {   // rhs_z may alias rhs_r (solve in place)
+                 const double* rhs_r, double* rhs_z, int R, long long batch_rhs_rows,     // rhs_z may alias rhs_r (solve in place)
+                 int diag_tiles_only) {                   // L_kk is scratch (batched fits): store only its diagonal 8 x 8 tiles
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x;
   K += blockIdx.x * batch_k;
@@ -102,7 +103,7 @@ potf2_inv_kernel(double* __restrict__ K, long long ldk, long long N, int kblk, d
     while (tj > ti) { tj -= ti + 1; ti++; }
     for (int t = warp; t < PACKED / 64; t += P2_WARPS) {
       const int i = ti * 8 + lg, c = tj * 8 + lq;
-      if (i < nv && c <= i) {
+      if (i < nv && c <= i && (!diag_tiles_only || ti == tj)) {
         const double2 v = *reinterpret_cast<const double2*>(sm + t * 64 + inoff);
         double* dst = K + (r0 + i) * ldk + r0 + c;
         if (c < i) *reinterpret_cast<double2*>(dst) = v; else *dst = v.x;
@@ -145,9 +146,9 @@ int launch_potf2(gpm_handle_impl* h, double* K, long long ldk, long long N, int 
   }
   // a lone block is latency-critical (16 warps); batches are throughput-bound (8 warps, two CTAs per SM)
   if (batch >= 64)
-    potf2_inv_kernel<256><<<batch, 256, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv, rhs_r, rhs_z, R, batch_rhs_rows);
+    potf2_inv_kernel<256><<<batch, 256, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv, rhs_r, rhs_z, R, batch_rhs_rows, h->scratch_factor ? 1 : 0);
   else
-    potf2_inv_kernel<512><<<batch, 512, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv, rhs_r, rhs_z, R, batch_rhs_rows);
+    potf2_inv_kernel<512><<<batch, 512, POTF2_SMEM, stream>>>(K, ldk, N, kblk, invD, info, batch_k, batch_inv, rhs_r, rhs_z, R, batch_rhs_rows, h->scratch_factor ? 1 : 0);
   GPM_LAUNCH_CHECK();
   return 0;
 }

@@ -230,6 +230,25 @@ def test_batched_fused_forward_matches_separate_solve():
         assert np.abs(l1.cpu().numpy() - l0.cpu().numpy()).max() < 1e-12 * np.abs(l_o).max()
 
 
+def test_batched_scratch_factor_store_is_bitwise_neutral():
+    """Tiled batched fits store only the diagonal 8 x 8 tiles of every L_kk (L is scratch there: the log-determinant reads
+    the diagonal, the backward pass inv(L_kk)); the result must be bitwise the one with the whole factor stored (option
+    no_scratch_factor), ragged last block and many right-hand sides included."""
+    for (B, N, D, R) in ((70, 300, 2, 3), (64, 512, 3, 1), (66, 130, 2, 8)):     # batch >= 64: the 8-warp batched potf2
+        Xb, Yb, th = wl.batched_paths(B, N, seed=6, D=D, R=2)
+        rng = np.random.default_rng(R)
+        Yb = np.ascontiguousarray(np.concatenate([Yb, Yb.std() * rng.standard_normal((B, N, 6))], axis=2)[:, :, :R])
+        with _native.option("no_path_fused", 1):
+            a1, l1 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+            a1, l1 = a1.clone(), l1.clone()
+            with _native.option("no_scratch_factor", 1):
+                a0, l0 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+        assert torch.equal(a1, a0) and torch.equal(l1, l0)
+        a_o, l_o = gp_ref.fit_batched(Xb[:3], Yb[:3], th)
+        assert nrm(a1[:3].cpu().numpy(), a_o) < MEAN_TOL
+        assert np.abs(l1[:3].cpu().numpy() - l_o).max() < LML_TOL * np.abs(l_o).max()
+
+
 def test_lml_sweep_vs_oracle():
     X, Y, _ = wl.single_path(180, seed=5, D=2, R=2)
     ths = wl.sweep_thetas(D=2)[::9]
