@@ -106,7 +106,10 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
     GPM_CUDA(cudaMemcpyAsync(tdev, theta, (size_t)B * (D + 2) * sizeof(double), cudaMemcpyHostToDevice, st));
     theta_dev = tdev;
   }
-  if ((rc = launch_cov(Xb, N, D, th, Kb, np, 1, (int)B, N * D, np * np, st, theta_dev, (int)theta_stride))) return rc;
+  // the upper 64 x 64 quadrant of a diagonal block has no reader in this pipeline (potf2 loads the packed lower triangle, the
+  // diagonal-tile updates compute and store only sub-tiles on / below the diagonal): not generated
+  const int lower_mode = h->opt.no_scratch_factor ? 1 : 2;
+  if ((rc = launch_cov(Xb, N, D, th, Kb, np, lower_mode, (int)B, N * D, np * np, st, theta_dev, (int)theta_stride))) return rc;
   // Paths short enough for the one-CTA-per-path solve: the forward substitution rides along with the
   // factorisation (alpha holds the running residual, zf receives z = L^{-1} Y), and the solve kernel only
   // runs the backward pass.

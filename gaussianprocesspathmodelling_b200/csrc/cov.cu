@@ -46,7 +46,9 @@ cov_kernel(const double* __restrict__ X, long long N, Theta th, double* __restri
   __syncthreads();
   const int c2 = (tid & 31) * 2;
   const bool diag = (ti == tj);
-  const bool mirror = !diag && (!lower_only || (ti >> 1) == (tj >> 1));
+  // lower_only: 1 = whole 128 x 128 tiles on / below the diagonal (the off-diagonal 64 x 64 tile of a diagonal 128-block is
+  // mirrored), 2 = nothing above the diagonal 64-tiles (batched fits: no consumer reads the upper quadrant of a diagonal block)
+  const bool mirror = !diag && (!lower_only || (lower_only == 1 && (ti >> 1) == (tj >> 1)));
   double bj0[3], bj1[3];
 #pragma unroll
   for (int d = 0; d < D; d++) { bj0[d] = xj[c2][d]; bj1[d] = xj[c2 + 1][d]; }

@@ -232,17 +232,22 @@ def test_batched_fused_forward_matches_separate_solve():
 
 def test_batched_scratch_factor_store_is_bitwise_neutral():
     """Tiled batched fits store only the diagonal 8 x 8 tiles of every L_kk (L is scratch there: the log-determinant reads
-    the diagonal, the backward pass inv(L_kk)); the result must be bitwise the one with the whole factor stored (option
-    no_scratch_factor), ragged last block and many right-hand sides included."""
+    the diagonal, the backward pass inv(L_kk)) and do not generate the upper 64 x 64 quadrant of the diagonal covariance
+    blocks; the result must be bitwise the one with the whole factor / whole tiles stored (option no_scratch_factor),
+    ragged last block and many right-hand sides included, on a NaN-filled workspace."""
     for (B, N, D, R) in ((70, 300, 2, 3), (64, 512, 3, 1), (66, 130, 2, 8)):     # batch >= 64: the 8-warp batched potf2
         Xb, Yb, th = wl.batched_paths(B, N, seed=6, D=D, R=2)
         rng = np.random.default_rng(R)
         Yb = np.ascontiguousarray(np.concatenate([Yb, Yb.std() * rng.standard_normal((B, N, 6))], axis=2)[:, :, :R])
+        npad = (N + 127) // 128 * 128
+        ws = torch.empty(B * (npad * npad + npad * 128 + 8 + npad * 8), dtype=torch.float64, device="cuda")
         with _native.option("no_path_fused", 1):
-            a1, l1 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+            ws.fill_(float("nan"))            # whatever is not generated / stored stays NaN: a stray reader would show
+            a1, l1 = GPmap.fit_gp_batched(Xb, Yb, theta=th, workspace=ws)
             a1, l1 = a1.clone(), l1.clone()
             with _native.option("no_scratch_factor", 1):
-                a0, l0 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+                ws.fill_(float("nan"))
+                a0, l0 = GPmap.fit_gp_batched(Xb, Yb, theta=th, workspace=ws)
         assert torch.equal(a1, a0) and torch.equal(l1, l0)
         a_o, l_o = gp_ref.fit_batched(Xb[:3], Yb[:3], th)
         assert nrm(a1[:3].cpu().numpy(), a_o) < MEAN_TOL
