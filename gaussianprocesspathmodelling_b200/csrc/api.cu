@@ -62,6 +62,7 @@ static const OptEntry kOptions[] = {
     {"path_fused", &Options::path_fused},         {"no_half_tiles", &Options::no_half_tiles},
     {"half_warps", &Options::half_warps},          {"half_stages", &Options::half_stages},
     {"no_split_column", &Options::no_split_column}, {"no_scratch_factor", &Options::no_scratch_factor},
+    {"batch_width", &Options::batch_width},
 };
 
 static void options_from_env(Options* o) {

@@ -74,6 +74,7 @@ struct Options {
   int half_warps = 8;        // half-tile kernel: warps per CTA (8: 32 x 32 warp tiles, four warps per scheduler; 4: 64 x 32)
   int no_half_tiles = 0;     // batched launches through the 128 x 128 tile kernel instead of the half-tile one
   int no_fused_fwd = 0;      // batched fits: separate forward substitution
+  int batch_width = 4;       // potrf, whole-batch launches: outer panel width in block columns (left-looking inside the panel; 4096 x 512: 10.90 / 10.69 / 10.66 ms at 1 / 2 / 4, 1024 x 1024: 15.27 / 15.12 / 15.18 ms at 2 / 4 / 8)
   int no_scratch_factor = 0; // batched fits: potf2 stores the whole lower triangle of L_kk although only its diagonal is read afterwards
   int no_fused_mean = 0;     // predict: separate mean kernel
   int var_steps = 0;         // variance: one launch per block column

@@ -270,14 +270,14 @@ int potrf_blocked(gpm_handle_impl* h, double* K, long long N, long long ldk, dou
   // hidden behind the rest-update: width 8 while >= 96 block columns remain, 4 while >= 64, 2 while >= 36,
   // then 1 (thresholds swept on B200 at N = 8192 and 16384, tools/potrf_sweep.sh and potrf_sweep2.sh; the response
   // is flat within 1 % around these values; 36 rather than 32 keeps N = 4096 all-narrow, tools/potrf_sweep3.sh).
-  // Large batches are throughput-bound in every launch, so they use width 2 and no look-ahead.
+  // Large batches are throughput-bound in every launch, so they use width 4 (option batch_width) and no look-ahead.
   const int wide_env = h->opt.wide_min, wide4_env = h->opt.wide4_min, wide8_env = h->opt.wide8_min;
   std::vector<int> pb(nblk + 1), pw(nblk + 1);
   int npanel = 0;
   for (int b = 0; b < nblk;) {
     const int left = nblk - b;
     int w = 1;
-    if (batch >= 32) w = left >= 2 ? 2 : 1;
+    if (batch >= 32) w = std::max(1, std::min(left, h->opt.batch_width));
     else if (left >= wide8_env) w = 8;
     else if (left >= wide4_env) w = 4;
     else if (left >= wide_env) w = 2;
