@@ -62,7 +62,7 @@ static const OptEntry kOptions[] = {
     {"path_fused", &Options::path_fused},         {"no_half_tiles", &Options::no_half_tiles},
     {"half_warps", &Options::half_warps},          {"half_stages", &Options::half_stages},
     {"no_split_column", &Options::no_split_column}, {"no_scratch_factor", &Options::no_scratch_factor},
-    {"batch_width", &Options::batch_width},
+    {"batch_width", &Options::batch_width},      {"small_two_max", &Options::small_two_max},
 };
 
 static void options_from_env(Options* o) {

@@ -27,7 +27,7 @@ int launch_lml(const double* L, long long N, long long ldl, const double* Y, con
 bool fit_small_supported(long long N);
 int launch_fit_small(const double* Xb, const double* Yb, long long B, long long N, int D, int R, const Theta& th,
                      const double* theta_dev, int theta_stride, double* alpha, double* lml, int* info,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int two_max);
 
 bool path_fit_supported(long long N, int R);
 size_t path_fit_workspace_bytes(const gpm_handle_impl* h, long long B, long long N);
@@ -91,7 +91,7 @@ extern "C" int gpm_fit_batched(gpm_handle_t handle, const double* Xb, const doub
       GPM_CUDA(cudaMemcpyAsync(ws, theta, (size_t)B * (D + 2) * sizeof(double), cudaMemcpyHostToDevice, st));
       tdev = reinterpret_cast<const double*>(ws);
     }
-    return launch_fit_small(Xb, Yb, B, N, D, R, th, tdev, (int)theta_stride, alpha, lml, info, st);
+    return launch_fit_small(Xb, Yb, B, N, D, R, th, tdev, (int)theta_stride, alpha, lml, info, st, h->opt.small_two_max);
   }
   if (fused)   // 112 < N <= 1024: one CTA per path, two paths in flight per SM, K never materialised (pathfit.cu)
     return launch_path_fit(h, Xb, Yb, B, N, D, R, th, theta_stride ? theta : nullptr, (int)theta_stride, alpha, lml, info, ws, st);

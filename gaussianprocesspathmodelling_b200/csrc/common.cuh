@@ -68,6 +68,7 @@ struct Options {
   int wide_min = 36, wide4_min = 64, wide8_min = 96;   // potrf: outer panel width thresholds (36: N = 4096, 32 block columns, is faster all-narrow: 2.00 vs 2.15 ms; N = 6144 keeps its wide start: 4.16 vs 4.30 ms; tools/potrf_sweep3.sh)
   int no_separable = 0;      // grid queries through the pointwise kernels
   int no_small_fused = 0;    // short paths through the tiled pipeline
+  int small_two_max = 12;    // short paths, 32 < N <= 32 + this: the rows beyond 32 ride as second rows of the first threads (0 = one thread per row always)
   int no_small_tiles = 0;    // no latency tile kernel
   int no_split_column = 0;   // look-ahead Cholesky: update the next panel's whole column before its diagonal block (no split)
   int half_stages = 0;       // half-tile kernel: cap on the ring depth of the plain-store launches (0 = auto: 4, or 3 with more than 4 right-hand sides)

@@ -695,6 +695,38 @@ def test_short_paths_one_cta_per_path_kernel():
     assert nrm(am[-3:].cpu().numpy(), a_o) < MEAN_TOL and bool(torch.isfinite(lm).all())
 
 
+def test_short_paths_second_row_threads():
+    """A path of 33 .. 44 samples (the reference's 33) runs on ONE warp, the first N - 32 threads of which own a second
+    row (fit_small_kernel<.., TWO>; option small_two_max).  Same arithmetic per element
+    as one thread per row: alpha and info bitwise, the LML to rounding of its (re-associated) final sum; and against
+    the oracle."""
+    for (B, N, D, R) in ((9, 33, 2, 2), (5, 34, 3, 1), (4, 40, 2, 3), (3, 36, 3, 8), (3, 44, 2, 4), (2, 45, 2, 1), (2, 65, 3, 2)):
+        Xb, Yb, th = wl.batched_paths(B, N, seed=21, D=D, R=2)
+        rng = np.random.default_rng(N)
+        Yb = np.ascontiguousarray(np.concatenate([Yb, rng.standard_normal((B, N, 6))], axis=2)[:, :, :R])
+        a1, l1 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+        with _native.option("small_two_max", 0):
+            a0, l0 = GPmap.fit_gp_batched(Xb, Yb, theta=th)
+        a_o, l_o = gp_ref.fit_batched(Xb, Yb, th)
+        assert torch.equal(a1, a0)
+        assert np.abs((l1 - l0).cpu().numpy()).max() < 1e-13 * max(np.abs(l_o).max(), 1.0)
+        assert nrm(a1.cpu().numpy(), a_o) < MEAN_TOL
+        assert np.abs(l1.cpu().numpy() - l_o).max() < LML_TOL * max(np.abs(l_o).max(), 1.0)
+    # pivots that fail in second rows (rows 33..35 duplicate rows 5..7, zero noise: a tiny pivot of either sign, then a
+    # negative one for certain), and in first rows
+    Xb, Yb, th = wl.batched_paths(5, 40, seed=12, D=2, R=2)
+    th0 = th.copy(); th0[-1] = 0.0
+    for (row, path) in ((33, 1), (20, 3)):
+        Xs = Xb.copy(); Xs[path, row:row + 3] = Xs[path, 5:8]
+        with pytest.raises(np.linalg.LinAlgError, match=f"path {path}") as ei:
+            GPmap.fit_gp_batched(Xs, Yb, theta=th0)
+        msg1 = str(ei.value)
+        with _native.option("small_two_max", 0):
+            with pytest.raises(np.linalg.LinAlgError, match=f"path {path}") as ei0:
+                GPmap.fit_gp_batched(Xs, Yb, theta=th0)
+        assert msg1 == str(ei0.value)           # same pivot index
+
+
 def test_latency_tile_kernel_is_bitwise_the_tile_kernel():
     """Launches of at most 37 tiles (every tile launch of a fit with N <= 4096, the tail of a large one) split each
     128x128 tile into four 64x64 quarters on four SMs (gemm_small.cu).  Same DMMA sequence per element: the factor must

@@ -1,11 +1,11 @@
 """Short-path fits (one CTA per path, fit_small_kernel): fits/s at the reference's path length and around it.
-usage: python tools/bench_short.py [B]"""
+usage: python tools/bench_short.py [B] [N ...]   (GPM_SMALL_TWO_MAX=0: one thread per row always)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gaussianprocesspathmodelling_b200 import GPmap, workloads as wl
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-for N in (16, 32, 33, 40, 64, 80, 112):
+for N in ([int(v) for v in sys.argv[2:]] or (16, 32, 33, 40, 64, 80, 112)):
     Xb, Yb, th = wl.batched_paths(B, N, seed=3, D=2, R=2)
     Xd, Yd = torch.from_numpy(Xb).cuda(), torch.from_numpy(Yb).cuda()
     for _ in range(3):
