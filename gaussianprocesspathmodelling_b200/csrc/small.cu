@@ -39,6 +39,9 @@ fit_small_kernel(const double* __restrict__ Xb, const double* __restrict__ Yb, i
   double* vs = piv + N;                     // [N][RR] the solved entry of the current substitution step
   double* red = vs + N * RR;                // [4][RR + 1] cross-warp reduction
   const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+  // a one-warp CTA (N <= 44) orders its shared-memory traffic with __syncwarp(): no trip to the barrier unit
+  const bool one_warp = nthr == 32;
+#define SM_SYNC() do { if (one_warp) __syncwarp(); else __syncthreads(); } while (0)
   const long long b = blockIdx.x;
   if (theta_dev) {                          // per-path hyper-parameters
     const double* t = theta_dev + b * theta_stride;
@@ -65,7 +68,7 @@ fit_small_kernel(const double* __restrict__ Xb, const double* __restrict__ Yb, i
 #pragma unroll
     for (int r = 0; r < RR; r++) y02[r] = y2[r] = (has2 && r < R) ? Y[i2 * R + r] : 0.0;
   }
-  __syncthreads();
+  SM_SYNC();
 
   // ---- covariance: the N(N+1)/2 entries of the lower triangle dealt evenly to the threads (same arithmetic as
   //      cov_kernel) ----
@@ -80,7 +83,7 @@ fit_small_kernel(const double* __restrict__ Xb, const double* __restrict__ Yb, i
     if (c == r) v += th.sn2;
     Kp[e] = v;
   }
-  __syncthreads();
+  SM_SYNC();
 
   // ---- Cholesky, left-looking: column j of L from the finished columns 0..j-1 (two barriers per column) ----
   int bad = 0;
@@ -114,7 +117,7 @@ fit_small_kernel(const double* __restrict__ Xb, const double* __restrict__ Yb, i
     if (TWO && j < e2) {                      // block-uniform
       if (both) sb = col_entry(i2, j);       // i2 >= 32 > j: never the diagonal
     }
-    __syncthreads();
+    SM_SYNC();
     if (act || both) {
       double d = piv[j];
       if (!(d > 0.0) || !(d < 1.0e300)) { if (!bad) bad = j + 1; d = 1.0; }
@@ -125,7 +128,7 @@ fit_small_kernel(const double* __restrict__ Xb, const double* __restrict__ Yb, i
       }
       if (both) Kp[tri(i2) + j] = sb * rinv;
     }
-    __syncthreads();
+    SM_SYNC();
   }
   // the thread that owns row N-1 takes part in every column (with one row or the other), so it saw the first bad pivot
   if (TWO ? (has2 && i2 == N - 1) : (i == N - 1)) info[b] = bad;
@@ -144,7 +147,7 @@ fit_small_kernel(const double* __restrict__ Xb, const double* __restrict__ Yb, i
         }
       }
     }
-    __syncthreads();
+    SM_SYNC();
     const int row = (i > j) ? i : (has2 ? i2 : 0);
     if (row > j && row < N) {
       const double l = Kp[tri(row) + j];
@@ -159,7 +162,7 @@ fit_small_kernel(const double* __restrict__ Xb, const double* __restrict__ Yb, i
       }
     }
   }
-  __syncthreads();
+  SM_SYNC();
   if constexpr (TWO) {                        // back to y = own row (z_i), y2 = second row (z_i2)
     if (has2) {
 #pragma unroll
@@ -177,7 +180,7 @@ fit_small_kernel(const double* __restrict__ Xb, const double* __restrict__ Yb, i
 #pragma unroll
       for (int r = 0; r < RR; r++) { y[r] *= dinv[j]; vs[j * RR + r] = y[r]; }
     }
-    __syncthreads();
+    SM_SYNC();
     if (i < j) {
       const double l = Kp[tri(j) + i];
 #pragma unroll
@@ -220,13 +223,15 @@ fit_small_kernel(const double* __restrict__ Xb, const double* __restrict__ Yb, i
     const double sv = warp_sum(part[r]);
     if (lane == 0) red[warp * (RR + 1) + r] = sv;
   }
-  __syncthreads();
+  SM_SYNC();
   if (tid < R) {
     double q = 0.0, ld = 0.0;
     for (int w = 0; w < nwarp; w++) { q += red[w * (RR + 1) + tid]; ld += red[w * (RR + 1) + RR]; }
     lmlb[b * R + tid] = -0.5 * q - ld - 0.5 * (double)N * 1.8378770664093453;   // log(2 pi)
   }
 }
+
+#undef SM_SYNC
 
 bool fit_small_supported(long long N) { return N >= 1 && N <= SMALL_MAX_N; }
 
