@@ -61,18 +61,23 @@ kmeans_assign_kernel(const double* __restrict__ pxT, const double* __restrict__ 
 //                       (__match_any_sync inside a warp, per-warp tables across the warps of a round); per-chunk counts
 //   scan    (one CTA)   exclusive scan of the counts over the chunks, per centroid; row offset of every centroid's region
 //   gather  (all SMs)   row p of (xs, ys, timestamp) -> row offset[c] + chunk_offset + rank of ONE ordered buffer
-//   sum     (k CTAs)    a centroid streams its contiguous region through shared memory (16-byte asynchronous copies,
-//                       two stages) and its 3n summing threads add the rows in order
+//   sum     (~148 CTAs) the 3n running sums of a centroid are independent chains: the row entries are cut into slices of W
+//                       (the ordered buffer is slice-major, [slice][row][W]) and every (centroid, slice) CTA streams its
+//                       own contiguous region through shared memory (TMA bulk copies, two stages) while its W summing
+//                       threads add the rows in order
 // History (P = 100000, n = 33, k = 8, per Lloyd iteration): each member's value loaded right before its addition
 // 5.1 ms (ncu: 13 GB/s, issue slots 2 %: one DRAM round trip per member); in-kernel ballot compaction + staged gather on
-// k SMs 1.1 ms; this version 0.56 ms = assignment 0.083 + rank 0.011 + scan 0.004 + gather 0.03 + sum 0.43.  The sum
-// streams 10 MB per centroid from DRAM through ONE SM at about 30 GB/s (stage sizes of 64 and 128 rows give 2.7 and
+// k SMs 1.1 ms; one CTA per centroid 0.56 ms = assignment 0.083 + rank 0.011 + scan 0.004 + gather 0.03 + sum 0.43.  That sum
+// streamed 10 MB per centroid from DRAM through ONE SM at about 30 GB/s (stage sizes of 64 and 128 rows give 2.7 and
 // 4.4 us per stage: 1 us of latency + bytes / 30 GB/s).  Measured on top and not kept, all at 0.55 - 0.65 ms: four
 // stages of 64 rows (three bulk copies in flight), bulk copies in 4 KB pieces (slower) or one per stage, sixteen loads
 // ahead of their additions in the inner loop, evict-first loads in the gather so that the ordered buffer stays in L2,
 // and a chain of 16 CTAs per centroid passing the running sums on (each CTA can prefetch only its two stages, so the
-// later stages of its segment still load on the chain).  A chain in which every CTA owns every 16th two-stage segment,
-// with the next one prefetched while the chain is elsewhere, is what would spread the stream over more SMs.
+// later stages of its segment still load on the chain).
+// Last session of round 2: the stream is spread over the SMs by COLUMNS instead -- the sums of different row entries never
+// meet, so (centroid, slice) CTAs need no hand-off at all: sum 0.43 -> 0.24 ms, iteration 0.56 -> 0.40 ms (1 M paths: 5.1 ->
+// 3.5 ms).  What is left of the sum is the serial chain of the LARGEST cluster (37549 of the 100000 paths in the bench:
+// 12.5 cycles per addition); the shift of the centroids moved to the finish kernel (distances in parallel, their sum in order).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int KM_CH = 2048;              // paths per chunk (one CTA of the rank / gather kernels)
 constexpr int KM_THREADS = 256, KM_WARPS = KM_THREADS / 32;
@@ -150,34 +155,42 @@ __global__ void __launch_bounds__(KM_THREADS)
 kmeans_gather_kernel(const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pt,
                      long long P, int n, int k, const int* __restrict__ assign, const int* __restrict__ lrank,
                      const int* __restrict__ choff, const long long* __restrict__ coff, double* __restrict__ G,
-                     const KmState* __restrict__ state) {
+                     const KmState* __restrict__ state, int W, long long rows_total) {
   if (state->converged) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long p = (long long)blockIdx.x * KM_WARPS + warp;       // a warp per path: every copy of the launch is independent
   if (p >= P) return;
   const int c = assign[p];
   const long long row = coff[c] + choff[(p / KM_CH) * k + c] + lrank[p];
-  double* dst = G + row * 3 * n;
   const long long src = p * n;
+  // entry w of the row (xs | ys | timestamp) -> column w % W of slice w / W
+  auto put = [&](int w, double v) {
+    const int sl = w / W;
+    G[((long long)sl * rows_total + row) * W + (w - sl * W)] = v;
+  };
   for (int i = lane; i < n; i += 32) {
-    dst[i] = px[src + i];
-    dst[n + i] = py[src + i];
-    dst[2 * n + i] = pt[src + i];
+    put(i, px[src + i]);
+    put(n + i, py[src + i]);
+    put(2 * n + i, pt[src + i]);
   }
 }
 
-// One CTA per centroid; thread w < 3n owns entry w of a row (xs | ys | timestamp).  cold / cnew: [3][k][n].
+// One CTA per (centroid, slice of W row entries): the 3n running sums of a centroid are independent chains, so the
+// entries (xs | ys | timestamp) are cut into slices and every slice streams its own [members][W] region on its own SM
+// (the ordered buffer is slice-major).  Thread w < W owns entry slice * W + w.  cold / cnew: [3][k][n].
 // An empty cluster keeps its previous centroid.
 __global__ void __launch_bounds__(KM_THREADS, 1)
 kmeans_update_kernel(const double* __restrict__ G, int n, int k, const long long* __restrict__ total,
                      const long long* __restrict__ coff, const double* __restrict__ cold, double* __restrict__ cnew,
-                     double* __restrict__ shift_c, const KmState* __restrict__ state, int stage_rows) {
+                     const KmState* __restrict__ state, int stage_rows, int W, long long rows_total) {
   if (state->converged) return;
-  extern __shared__ __align__(16) double km_stage[];      // [2][stage_rows][3n]
-  const int c = blockIdx.x, tid = threadIdx.x;
-  const int work = 3 * n;
+  extern __shared__ __align__(16) double km_stage[];      // [2][stage_rows][W]
+  const int c = blockIdx.x, sl = blockIdx.y, tid = threadIdx.x;
+  const int work = W;                                      // row length of the slice (even: rows are 16-byte multiples)
+  const int w0 = sl * W;                                   // first entry of the slice
+  const int live = 3 * n - w0 < W ? 3 * n - w0 : W;        // entries of the slice that exist (the last slice may be padded)
   const long long m = total[c];
-  const double* region = G + coff[c] * work;               // 16-byte aligned: coff is even and so is stage_rows
+  const double* region = G + ((long long)sl * rows_total + coff[c]) * work;
   // each thread carries up to SLOTS running sums (entries tid, tid + KM_THREADS, ...)
   constexpr int SLOTS = 2048 / KM_THREADS;                 // 3 n <= 2048
   double sum[SLOTS];
@@ -185,8 +198,7 @@ kmeans_update_kernel(const double* __restrict__ G, int n, int k, const long long
   for (int s = 0; s < SLOTS; s++) sum[s] = 0.0;
   // rows [g0, g0 + cnt) of the region into stage `buf`: contiguous, so ONE thread moves them with bulk asynchronous
   // copies (TMA, completion counted in bytes on the stage's mbarrier).  Plain or cp.async loads top out near 20 GB/s
-  // for a single SM (ncu on the previous version: 164 GB/s over the 8 busy SMs); an odd row count is rounded up to
-  // 16 bytes and reads eight bytes into the next row, which exists: the buffer is padded.
+  // for a single SM (ncu on the one-CTA-per-centroid version: 164 GB/s over the 8 busy SMs).
   __shared__ __align__(8) unsigned long long km_bar[2];
   const uint32_t bar0 = smem_u32(&km_bar[0]);
   if (tid == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); fence_mbar_init(); }
@@ -218,13 +230,33 @@ kmeans_update_kernel(const double* __restrict__ G, int n, int k, const long long
 #pragma unroll 1
     for (int s = 0; s < SLOTS; s++) {
       const int w = tid + KM_THREADS * s;
-      if (w >= work) break;
+      if (w >= live) break;
       double acc = 0.0;
 #pragma unroll
       for (int t = 0; t < SLOTS; t++) if (t == s) acc = sum[t];
       const double* col = sb + w;
-#pragma unroll 8
-      for (int r = 0; r < cnt; r++) acc = __dadd_rn(acc, col[(size_t)r * work]);
+      // the additions are one dependent chain (member order: bit-exact with the reference; 8.3 cycles per DADD), so a value
+      // is reloaded for the row eight further on right after its addition: loads, address arithmetic and loop control
+      // issue in the shadow of the chain instead of between two groups of additions (12.4 -> ~9 cycles per row)
+      int r = 0;
+      if (cnt >= 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = col[(size_t)u * work];
+        const double* nx = col + (size_t)8 * work;
+        for (; r + 16 <= cnt; r += 8) {
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            acc = __dadd_rn(acc, v[u]);
+            v[u] = *nx;
+            nx += work;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, v[u]);
+        r += 8;
+      }
+      for (; r < cnt; r++) acc = __dadd_rn(acc, col[(size_t)r * work]);
 #pragma unroll
       for (int t = 0; t < SLOTS; t++) if (t == s) sum[t] = acc;
     }
@@ -234,25 +266,38 @@ kmeans_update_kernel(const double* __restrict__ G, int n, int k, const long long
 #pragma unroll
   for (int s = 0; s < SLOTS; s++) {
     const int w = tid + KM_THREADS * s;
-    if (w >= work) break;
-    const int a = w / n, i = w - a * n;
+    if (w >= live) break;
+    const int wg = w0 + w, a = wg / n, i = wg - a * n;
     const long long off = ((long long)a * k + c) * n + i;
     cnew[off] = cnt > 0 ? sum[s] / (double)cnt : cold[off];
   }
-  __syncthreads();
-  if (tid == 0) {                          // calc_distance(new_c, old_c): sequential, as the reference
-    double s = 0.0;
-    for (int i = 0; i < n; i++) {
-      const double dx = cnew[(long long)c * n + i] - cold[(long long)c * n + i];
-      const double dy = cnew[((long long)k + c) * n + i] - cold[((long long)k + c) * n + i];
-      s = __dadd_rn(s, sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
-    }
-    shift_c[c] = s;
-  }
 }
 
-__global__ void kmeans_finish_kernel(const double* __restrict__ shift_c, int k, double threshold, KmState* state) {
-  if (threadIdx.x != 0 || state->converged) return;
+// shift = sum_c calc_distance(new_c, old_c): a thread per centroid walks its samples sequentially, as the reference
+// does (GPmap.py:114-121), then thread 0 adds the k distances in centroid order.
+__global__ void __launch_bounds__(1024)
+kmeans_finish_kernel(const double* __restrict__ cold, const double* __restrict__ cnew, int n, int k,
+                     double* __restrict__ shift_c, double threshold, KmState* state) {
+  if (state->converged) return;
+  extern __shared__ double km_d[];         // [warps][n]: the point distances of one centroid per warp
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  double* d = km_d + (size_t)warp * n;
+  for (int c = warp; c < k; c += nwarp) {  // the distances in parallel, their sum in sample order
+    for (int i = lane; i < n; i += 32) {
+      const double dx = cnew[(long long)c * n + i] - cold[(long long)c * n + i];
+      const double dy = cnew[((long long)k + c) * n + i] - cold[((long long)k + c) * n + i];
+      d[i] = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double s = 0.0;
+      for (int i = 0; i < n; i++) s = __dadd_rn(s, d[i]);
+      shift_c[c] = s;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   double s = 0.0;
   for (int c = 0; c < k; c++) s = __dadd_rn(s, shift_c[c]);
   state->shift = s;
@@ -290,11 +335,20 @@ extern "C" int gpm_kmeans_assign(gpm_handle_t h, const double* pxT, const double
 //   ordered row buffer G [(P + 2k + 2)][3n]
 struct KmLayout {
   size_t shift_off, state_off, total_off, coff_off, lrank_off, counts_off, choff_off, g_off, bytes;
-  long long nchunks;
+  long long nchunks, rows_total;
+  int slices, W;            // the 3n row entries in `slices` slices of W (even) entries: slices * k CTAs ~ one per SM
 };
 static KmLayout km_layout(long long P, int n, int k) {
   KmLayout L;
   L.nchunks = (P + KM_CH - 1) / KM_CH;
+  {
+    const int work = 3 * n, want = std::max(1, 148 / k);   // B200: 148 SMs (k = 8, P = 100000: 8 / 32 / 64 / 148 / 296 / 600 CTAs give 0.70 / 0.47 / 0.42 / 0.40 / 0.39 / 0.39 ms per iteration)
+    int W = (work + want - 1) / want;
+    W = std::max(4, (W + 3) & ~3);                         // rows of whole 32-byte sectors (the gather writes them one by one)
+    L.W = W;
+    L.slices = (work + W - 1) / W;
+    L.rows_total = P + 2 * (long long)k + 2;
+  }
   size_t o = (size_t)3 * k * n * 8;
   L.shift_off = o; o += (size_t)k * 8;
   L.state_off = o; o += 16;
@@ -304,7 +358,7 @@ static KmLayout km_layout(long long P, int n, int k) {
   L.counts_off = o; o += (size_t)L.nchunks * k * 4;
   L.choff_off = o; o += (size_t)L.nchunks * k * 4;
   o = (o + 15) & ~(size_t)15;
-  L.g_off = o; o += (size_t)(P + 2 * (long long)k + 2) * 3 * n * 8;
+  L.g_off = o; o += (size_t)L.rows_total * L.slices * L.W * 8;
   L.bytes = o;
   return L;
 }
@@ -346,14 +400,18 @@ extern "C" int gpm_kmeans_lloyd(gpm_handle_t h, const double* px, const double* 
   if (smem > 48 * 1024)
     GPM_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t plane = (size_t)k * n;
-  // staged rows of the centroid sum: two stages of up to 128 rows (an even number) of 3n doubles, within 200 KB
-  int stage_rows = (int)std::max<size_t>(2, std::min<size_t>(128, (100 * 1024) / ((size_t)3 * n * 8)));
+  // staged rows of the centroid sum: two stages of about 48 KB (an even number of rows of W doubles)
+  int stage_rows = (int)std::max<size_t>(2, std::min<size_t>(4096, (48 * 1024) / ((size_t)L.W * 8)));
   stage_rows &= ~1;
-  const size_t upd_smem = (size_t)2 * stage_rows * 3 * n * sizeof(double) + 16;
+  const size_t upd_smem = (size_t)2 * stage_rows * L.W * sizeof(double) + 16;
   GPM_CUDA(cudaFuncSetAttribute(kmeans_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
   const size_t rank_smem = (size_t)(KM_WARPS + 1) * k * sizeof(int);
   if (rank_smem > 48 * 1024)
     GPM_CUDA(cudaFuncSetAttribute(kmeans_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
+  const int fin_threads = 32 * std::min(32, k);             // a warp per centroid (up to 32 at a time)
+  const size_t fin_smem = (size_t)(fin_threads / 32) * n * sizeof(double);
+  if (fin_smem > 48 * 1024)
+    GPM_CUDA(cudaFuncSetAttribute(kmeans_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
   const unsigned nchunks = (unsigned)L.nchunks;
   // Iterations ping-pong between `centroids` (even) and the workspace buffer (odd).  Once `converged` is set every
   // later kernel is a no-op, so state->iters tells the caller which buffer holds the final centroids; an even
@@ -368,11 +426,11 @@ extern "C" int gpm_kmeans_lloyd(gpm_handle_t h, const double* px, const double* 
     GPM_LAUNCH_CHECK();
     kmeans_scan_kernel<<<1, 1024, 0, st>>>(counts, (int)nchunks, k, choff, total, coff, state);
     GPM_LAUNCH_CHECK();
-    kmeans_gather_kernel<<<(unsigned)((P + KM_WARPS - 1) / KM_WARPS), KM_THREADS, 0, st>>>(px, py, pt, P, n, k, assign, lrank, choff, coff, G, state);
+    kmeans_gather_kernel<<<(unsigned)((P + KM_WARPS - 1) / KM_WARPS), KM_THREADS, 0, st>>>(px, py, pt, P, n, k, assign, lrank, choff, coff, G, state, L.W, L.rows_total);
     GPM_LAUNCH_CHECK();
-    kmeans_update_kernel<<<k, KM_THREADS, upd_smem, st>>>(G, n, k, total, coff, cur, nxt, shift_c, state, stage_rows);
+    kmeans_update_kernel<<<dim3(k, L.slices), KM_THREADS, upd_smem, st>>>(G, n, k, total, coff, cur, nxt, state, stage_rows, L.W, L.rows_total);
     GPM_LAUNCH_CHECK();
-    kmeans_finish_kernel<<<1, 32, 0, st>>>(shift_c, k, threshold, state);
+    kmeans_finish_kernel<<<1, fin_threads, fin_smem, st>>>(cur, nxt, n, k, shift_c, threshold, state);
     GPM_LAUNCH_CHECK();
   }
   return 0;
