@@ -37,18 +37,32 @@ kmeans_assign_kernel(const double* __restrict__ pxT, const double* __restrict__ 
   if (p >= P) return;
   double best = 0.0;
   int best_c = 0;
-  for (int c = 0; c < k; c++) {
-    const double* ccx = sc + c * n;
-    const double* ccy = sc + k * n + c * n;
-    double s = 0.0;
-#pragma unroll 4
+  // eight centroids at a time: a sample of the path is loaded once for the eight (the path's 2n values were re-read
+  // from L2 for every centroid: 422 MB per assignment at P = 100000, k = 8), the eight sqrt chains interleave; every
+  // distance is still summed sequentially in sample order, and the minimum scans the centroids in order
+  constexpr int KC = 8;
+  for (int c0 = 0; c0 < k; c0 += KC) {
+    double s[KC];
+#pragma unroll
+    for (int u = 0; u < KC; u++) s[u] = 0.0;
+    const double* ccx = sc + c0 * n;
+    const double* ccy = sc + k * n + c0 * n;
     for (int i = 0; i < n; i++) {
-      const double dx = pxT[(long long)i * P + p] - ccx[i];
-      const double dy = pyT[(long long)i * P + p] - ccy[i];
-      s = __dadd_rn(s, sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+      const double x = pxT[(long long)i * P + p], y = pyT[(long long)i * P + p];
+#pragma unroll
+      for (int u = 0; u < KC; u++)
+        if (c0 + u < k) {
+          const double dx = x - ccx[u * n + i];
+          const double dy = y - ccy[u * n + i];
+          s[u] = __dadd_rn(s[u], sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+        }
     }
-    if (dist) dist[p * k + c] = s;
-    if (c == 0 || s < best) { best = s; best_c = c; }
+#pragma unroll
+    for (int u = 0; u < KC; u++)
+      if (c0 + u < k) {
+        if (dist) dist[p * k + c0 + u] = s[u];
+        if (c0 + u == 0 || s[u] < best) { best = s[u]; best_c = c0 + u; }
+      }
   }
   assign[p] = best_c;
 }
