@@ -313,6 +313,31 @@ def test_kmeans_device_lloyd_matches_the_reference_run():
     assert T.kmeans_iterations >= 1 and all(np.isfinite(c.xs).all() for c in T.centroids.values())
 
 
+def test_kmeans_many_clusters_against_the_restated_loop():
+    """More clusters than one assignment pass takes (eight per pass), sliced centroid sums (k = 20: seven slices of 16
+    row entries; k = 150: one slice per centroid) and clusters spanning several 2048-path chunks, against the oracle's
+    restatement of the reference's loops (pinned by the reference-golden tests): same assignment, bit-identical
+    centroids after the same number of iterations."""
+    for (P, k, iters) in ((5000, 20, 2), (600, 150, 2)):
+        xs, ys, ts = wl.trajectory_families(P, min(k, 12), 33, seed=31)
+        T = GPmap.trajectories()
+        for i in range(P):
+            t = GPmap.trajectory(); t.xs, t.ys, t.timestamp = xs[i], ys[i], ts[i]
+            T.add_trajectory(i, t)
+        init = list(range(0, P, P // k))[:k]
+        clusters = T.kmeansclustering(k, init=init, max_iter=iters)
+        a_o, c_o, it_o = gp_ref.lloyd(xs, ys, ts, init, threshold=5.0, max_iter=iters)
+        assert T.kmeans_iterations == it_o
+        names = list(clusters)
+        got = np.full(P, -1)
+        for c, nm in enumerate(names):
+            got[clusters[nm]] = c
+        assert np.array_equal(got, a_o)
+        cents = np.stack([np.stack([T.centroids[nm].xs for nm in names]), np.stack([T.centroids[nm].ys for nm in names]),
+                          np.stack([T.centroids[nm].timestamp for nm in names])])
+        assert np.array_equal(cents, c_o)
+
+
 def test_config2_size_against_oracle_and_properties():
     # N=4096 fit compared with the oracle directly (about a second of CPU), prediction on a strided
     # sample of the 512x512 grid, plus size-independent properties of the full grid.
